@@ -1,0 +1,140 @@
+/* msm_b200.h — C ABI of the B200-native cost-evaluation path of newMSM (rbesenczi/msm-newmeshreg).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Every entry
+ * point cites the reference interface it replaces (paths relative to the reference tree).  The host-side C++
+ * mirror of the reference classes (msm_newmeshreg_b200/host/) is a thin layer over these calls.
+ *
+ * Conventions
+ *  - All host arrays are caller-owned; the context owns every device buffer.  One context per GPU; a context
+ *    is NOT thread-safe (one host thread drives it), table look-ups on the host side are.
+ *  - Coordinates are double[n][3] on the sphere of radius 100 (RAD, src/DiscreteCostFunction.h:9).
+ *  - Feature matrices are channel-major double[C][V], i.e. FEAT->get_ref_val(d+1, v+1) == ref[d*V + v]
+ *    (src/featurespace.h:30-32).
+ *  - Table layouts are the reference's: unary[label*N + node] (src/DiscreteCostFunction.cpp:312),
+ *    pair[pair*L*L + labelB*L + labelA] (:303), triplet[((t*L + la)*L + lb)*L + lc].
+ *  - Every function returns 0 on success, non-zero on error; msm_last_error() gives the message.
+ *    There is NO CPU fallback: without a CUDA device msm_create fails.
+ */
+#ifndef MSM_B200_H
+#define MSM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct msm_ctx msm_ctx;
+
+/* NonLinearSRegDiscreteCostFunction::set_parameters (src/DiscreteCostFunction.cpp:121-136) plus the scalars the
+ * model hands over through set_spacings (src/DiscreteCostFunction.h:178) and set_initial_angles (:95-102). */
+typedef struct msm_params {
+    double lambda;     /* "lambda"          _reglambda */
+    double rexp;       /* "exponent"        _rexp      */
+    double mu;         /* "shearmodulus"    _mu        */
+    double kappa;      /* "bulkmodulus"     _kappa     */
+    double k_exp;      /* "kexponent"       _k_exp     */
+    double range;      /* "range"           _controlptrange */
+    int simmeasure;    /* "simmeasure": sign of the unary term (:444-447, :522-525) */
+    int rmode;         /* "regularisermode": 2 angular, 3 strain (:170-201); 1 = pairwise model */
+    int dweight;       /* "weight"  (:182) */
+    int anorm;         /* "anorm"   (:190) */
+    double meanangle;  /* _MEANANGLE (:101) */
+    double mvdmax;     /* MVDmax (set_spacings) — pairwise regulariser (:262) */
+    int group;         /* 0: NonLinearSRegDiscreteCostFunction; 1: DiscreteGroupCostFunction triplet rules
+                          (fold -> 1e7, k_exp forced to 2, src/DiscreteGroupCostFunction.cpp:23,29) */
+    int bary_orthogonal; /* A4 switch: 0 radial projection (default), 1 orthogonal — locate/unary */
+} msm_params;
+
+void msm_default_params(msm_params* p);
+
+/* lifetime ------------------------------------------------------------------------------------------------ */
+int msm_create(int device, msm_ctx** out);
+void msm_destroy(msm_ctx* ctx);
+const char* msm_last_error(const msm_ctx* ctx); /* ctx may be NULL: last creation error */
+/* Use an existing CUDA stream (cudaStream_t as void*); NULL = the context's own stream. */
+int msm_set_stream(msm_ctx* ctx, void* cuda_stream);
+int msm_synchronize(msm_ctx* ctx);
+
+/* set_parameters (src/DiscreteCostFunction.cpp:121-136) */
+int msm_set_params(msm_ctx* ctx, const msm_params* p);
+
+/* set_meshes/_TARGET + set_featurespace/get_ref_val + set_octrees (src/DiscreteCostFunction.h:166-180,
+ * src/DiscreteModel.cpp:88): the target must be a regular icosphere (the reference always resamples data onto
+ * one: src/featurespace.cc:27-31,46); any vertex/face numbering and orientation is accepted — the icosahedral
+ * hierarchy that replaces the Octree is rebuilt from the geometry.  feat may be NULL (locate only). */
+int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int F, const double* feat, int C);
+
+/* set_meshes/_SOURCE + FEAT->get_input_val + set_dataaffintyweighting (src/DiscreteCostFunction.h:144,166-168).
+ * cfweight: double[wrows][V] with wrows in {0,1,C}; missing rows weigh 1.0 (:404-407,:474-477).
+ * multivariate selects the Multivariate cost function (src/DiscreteModel.cpp:22-36). */
+int msm_set_source(msm_ctx* ctx, const double* xyz, int V, const double* feat, int C, const double* cfweight, int wrows,
+                   int multivariate);
+/* reset_source (src/DiscreteCostFunction.h:181): new coordinates of the deforming source mesh. */
+int msm_reset_source(msm_ctx* ctx, const double* xyz);
+
+/* set_meshes/_CPgrid,_oCPgrid,_ORIG + set_spacings (src/DiscreteCostFunction.h:166-168,178).
+ * orig_xyz = _ORIG coordinates indexed by CP id (nested numbering, :175-177,:195-197); NULL = xyz.
+ * abs_weights = AbsoluteWeights per CP (resample_weights :364-383, [EXT] metric_resample); NULL = all 1. */
+int msm_set_cpgrid(msm_ctx* ctx, const double* xyz, int N, const int* tris, int T, const double* maxsep,
+                   const double* orig_xyz, const double* abs_weights);
+/* reset_CPgrid (src/DiscreteCostFunction.h:182) */
+int msm_reset_cpgrid(msm_ctx* ctx, const double* xyz);
+/* Multi-GPU: this context evaluates unary rows / patches only for CPs [k_begin,k_end). */
+int msm_set_shard(msm_ctx* ctx, int k_begin, int k_end);
+
+/* set_labels(labels, ROT) (src/DiscreteCostFunction.h:170-173).  ROT[k] = rotation(centre -> CP_k) is
+ * recomputed on the device from `centre` and the current CP grid (src/DiscreteModel.cpp:284-294). */
+int msm_set_labels(msm_ctx* ctx, const double* labels, int L, const double* centre);
+
+/* setPairs / setTriplets (src/DiscreteCostFunction.h:25-26): int[2P] / int[3T], ids sorted ascending. */
+int msm_set_pairs(msm_ctx* ctx, const int* pairs, int P);
+int msm_set_triplets(msm_ctx* ctx, const int* triplets, int T);
+/* Group model (src/DiscreteGroupCostFunction.h:11-19): S subjects x N_subj control points; cp grid passed to
+ * msm_set_cpgrid is the concatenation [S*N_subj]; _ORIG is indexed by the per-subject id. */
+int msm_set_group(msm_ctx* ctx, int S, int N_subj, int T_subj);
+
+/* get_source_data (src/DiscreteCostFunction.cpp:394-410 / :458-481): builds the per-CP patch lists for the
+ * current source and CP coordinates.  Exact-tie pairs are resolved with the reference's own fp64 formula. */
+int msm_build_patches(msm_ctx* ctx);
+/* _sourceinrange as CSR: offsets int[N+1] (only this shard's rows are non-empty), idx int[total]. */
+int msm_patch_count(msm_ctx* ctx, long long* total);
+int msm_get_patches(msm_ctx* ctx, int* offsets, int* idx);
+
+/* computeUnaryCosts (src/DiscreteCostFunction.cpp:306-313): out double[L][N] (rows of other shards untouched). */
+int msm_unary_table(msm_ctx* ctx, double* out);
+/* Device-resident variant: d_out = float[L][k_end-k_begin] in device memory, launched on the ctx stream. */
+int msm_unary_table_dev(msm_ctx* ctx, float* d_out);
+
+/* computeTripletCost (src/DiscreteCostFunction.cpp:138-254; group: src/DiscreteGroupCostFunction.cpp:9-30).
+ *  _costs : n arbitrary queries q[n][4] = (triplet, la, lb, lc)
+ *  _table : full float[T1-T0][L][L][L] look-up table for triplets [t0,t1) (serves unmodified Fusion::optimize)
+ *  _moves : the 8 fusion-move costs of include/Fusion/Fusion.h:187-194 for every triplet, for label alpha
+ *           (out double[T][8]) or, with alpha = -1, for all labels (out double[L][T][8]). */
+int msm_triplet_costs(msm_ctx* ctx, int n, const int* q, double* out);
+int msm_triplet_table(msm_ctx* ctx, int t0, int t1, float* out);
+int msm_triplet_table_dev(msm_ctx* ctx, int t0, int t1, float* d_out);
+int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out);
+int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float* d_out);
+
+/* computePairwiseCosts (src/DiscreteCostFunction.cpp:256-304): out float[P][L][L] in the reference layout. */
+int msm_pair_table(msm_ctx* ctx, float* out);
+int msm_pair_table_dev(msm_ctx* ctx, float* d_out);
+
+/* Octree::get_closest_triangle + barycentric weights on the target ([EXT] A3/A4; call sites
+ * src/DiscreteCostFunction.cpp:421-433).  tri = index into the `tris` given to msm_set_target; w double[M][3]
+ * in that triangle's vertex order. */
+int msm_locate(msm_ctx* ctx, const double* pts, int M, int* tri, double* w);
+
+/* evaluateTotalCostSum (src/DiscreteCostFunction.cpp:41-70) from the device tables of the last *_table calls:
+ * sums[0..2] = unary, pairwise, triplet; requires msm_unary_table(_dev) to have run. */
+int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]);
+
+/* Introspection for bench/tests: number of kernels this library launched so far, and per-kernel timing of the
+ * last call of the named kernel family measured with CUDA events on the ctx stream (ms, <0 if none). */
+long long msm_launch_count(const msm_ctx* ctx);
+int msm_set_timing(msm_ctx* ctx, int enabled);
+double msm_last_kernel_ms(const msm_ctx* ctx, const char* family);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSM_B200_H */

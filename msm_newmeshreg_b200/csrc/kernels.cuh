@@ -1,0 +1,632 @@
+// kernels.cuh — sm_100a kernels of the newMSM cost-evaluation hot path.
+// No tensor cores: nothing here is a dense contraction (north_star).  Everything is gather / scan / reduce work.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "locate.cuh"
+
+namespace msm {
+
+constexpr double kRAD = 100.0;      // src/DiscreteCostFunction.h:9
+constexpr double kEPSILON = 1.0e-8; // src/DiscreteCostFunction.h:10
+
+struct DevParams {
+    double lambda, rexp, mu, kappa, k_exp, range, meanangle, mvdmax;
+    int simmeasure, rmode, dweight, anorm, group;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// =========================================================================================================
+// k_label_rot — per (control point, label):  disp = ROT[k]*label_l  (ROT[k] = rot(centre -> CP_k),
+// src/DiscreteModel.cpp:284-294) and K = rot(CP_k -> disp) - I (src/DiscreteCostFunction.cpp:439,513,258-259).
+// One thread per (k,l); fp64 (B200 has full-rate-class FP64), results kept in fp64 and fp32.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_label_rot(int N, int L, const double* __restrict__ cp, const double* __restrict__ labels,
+                                                   double cx, double cy, double cz, double* __restrict__ disp,
+                                                   float* __restrict__ Kf, double* __restrict__ Kd) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= N * L) return;
+    int k = id / L, l = id - k * L;
+    double c[3] = {cx, cy, cz};
+    double p[3] = {cp[3 * k], cp[3 * k + 1], cp[3 * k + 2]};
+    double K[9];
+    rodrigues_minus_identity(c, p, K);
+    double lx = labels[3 * l], ly = labels[3 * l + 1], lz = labels[3 * l + 2];
+    double d[3];
+    d[0] = lx + (K[0] * lx + K[1] * ly + K[2] * lz);
+    d[1] = ly + (K[3] * lx + K[4] * ly + K[5] * lz);
+    d[2] = lz + (K[6] * lx + K[7] * ly + K[8] * lz);
+    disp[3 * id] = d[0]; disp[3 * id + 1] = d[1]; disp[3 * id + 2] = d[2];
+    rodrigues_minus_identity(p, d, K);
+#pragma unroll
+    for (int i = 0; i < 9; i++) Kf[(size_t)id * 9 + i] = (float)K[i];
+    if (Kd) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) Kd[(size_t)id * 9 + i] = K[i];
+    }
+}
+
+// =========================================================================================================
+// Patch construction — get_source_data / within_controlpt_range (src/DiscreteCostFunction.cpp:104-109,394-410,458-481)
+// geod(CP_k, SRC_i) < range*MAXSEP_k  <=>  chord < 2R sin(range*MAXSEP_k / 2R).  fp32 pre-filter, fp64 decision with
+// an uncertainty band of 1e-11 relative; pairs inside the band go to the host, which applies the reference's own
+// asin formula, so membership is identical to the reference even at the exact ties of an undeformed icosphere.
+// =========================================================================================================
+struct PatchArgs {
+    int k_begin, k_end, V;
+    const float* sxf; const float* syf; const float* szf;    // source xyz fp32 SoA
+    const double* src;                                       // source xyz fp64 [V][3]
+    const double* cp;                                        // CP xyz fp64 [N][3]
+    const double* maxsep;                                    // [N]
+    double range;
+    int* counts;                                             // [Ns] definite members
+    int2* unc; int unc_cap; int* unc_count;                  // uncertain (k,i) pairs
+    const int* acc_off; const int* acc_idx;                  // accepted uncertain pairs per shard row (fill pass)
+    const int* off;                                          // [Ns+1] CSR offsets (fill pass)
+    int* idx;                                                // [total]
+};
+
+__device__ __forceinline__ void patch_thresholds(double thr, double& c2lo, double& c2hi, float& c2f) {
+    double h = thr / (2.0 * kRAD);
+    if (h >= 1.5707963267948966) { c2lo = 1e300; c2hi = 1e300; c2f = 3.0e38f; return; }
+    double c = 2.0 * kRAD * sin(h);
+    double lo = c * (1.0 - 1e-11), hi = c * (1.0 + 1e-11);
+    c2lo = lo * lo; c2hi = hi * hi;
+    c2f = (float)(c * c * (1.0 + 1e-4) + 1e-6);
+}
+
+// classify vertex i against CP k: 0 out, 1 in, 2 uncertain
+__device__ __forceinline__ int patch_classify(const PatchArgs& a, int i, double cx, double cy, double cz, float cxf, float cyf, float czf,
+                                              double c2lo, double c2hi, float c2f) {
+    float dx = a.sxf[i] - cxf, dy = a.syf[i] - cyf, dz = a.szf[i] - czf;
+    float d2f = dx * dx + dy * dy + dz * dz;
+    if (d2f > c2f) return 0;
+    double ex = cx - a.src[3 * i], ey = cy - a.src[3 * i + 1], ez = cz - a.src[3 * i + 2];
+    double d2 = ex * ex + ey * ey + ez * ez;
+    if (d2 < c2lo) return 1;
+    if (d2 <= c2hi) return 2;
+    return 0;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_patch(PatchArgs a) {
+    const int row = blockIdx.x;
+    const int k = a.k_begin + row;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const double cx = a.cp[3 * k], cy = a.cp[3 * k + 1], cz = a.cp[3 * k + 2];
+    const float cxf = (float)cx, cyf = (float)cy, czf = (float)cz;
+    double c2lo, c2hi; float c2f;
+    patch_thresholds(a.range * a.maxsep[k], c2lo, c2hi, c2f);
+    // the fp32 pre-filter compares against rounded coordinates: widen by the rounding of |x|<=~100 inputs
+    c2f += 1e-2f;
+    int acc0 = 0, acc1 = 0;
+    if (FILL && a.acc_off) { acc0 = a.acc_off[row]; acc1 = a.acc_off[row + 1]; }
+    if (tid == 0) s_base = FILL ? a.off[row] : 0;
+    __syncthreads();
+    int total = 0;
+    for (int base = 0; base < a.V; base += 256) {
+        int i = base + tid;
+        int cls = 0;
+        if (i < a.V) cls = patch_classify(a, i, cx, cy, cz, cxf, cyf, czf, c2lo, c2hi, c2f);
+        bool in = (cls == 1);
+        if (cls == 2) {
+            if (!FILL) {
+                int slot = atomicAdd(a.unc_count, 1);
+                if (slot < a.unc_cap) a.unc[slot] = make_int2(k, i);
+            } else {
+                for (int e = acc0; e < acc1; e++)
+                    if (a.acc_idx[e] == i) { in = true; break; }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, in);
+        if (!FILL) {
+            if (lane == 0) total += __popc(m);
+        } else {
+            if (lane == 0) s_warp[warp] = __popc(m);
+            __syncthreads();
+            int before = 0, all = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { int c = s_warp[w]; if (w < warp) before += c; all += c; }
+            if (in) a.idx[s_base + before + __popc(m & ((1u << lane) - 1u))] = i;
+            __syncthreads();
+            if (tid == 0) s_base += all;
+            __syncthreads();
+        }
+    }
+    if (!FILL) {
+        if (lane == 0) s_warp[warp] = total;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w = 0; w < 8; w++) t += s_warp[w];
+            a.counts[row] = t;
+        }
+    }
+}
+
+// exclusive scan of (counts + accepted) over the shard rows; also total and max.  Single CTA.
+__global__ void __launch_bounds__(1024) k_patch_scan(int n, const int* __restrict__ counts, const int* __restrict__ acc_off,
+                                                     int* __restrict__ off, int* __restrict__ total_max) {
+    __shared__ int s[1024];
+    __shared__ int s_carry, s_max;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_carry = 0; s_max = 0; }
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + tid;
+        int c = 0;
+        if (i < n) c = counts[i] + (acc_off ? (acc_off[i + 1] - acc_off[i]) : 0);
+        s[tid] = c;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int v = (tid >= o) ? s[tid - o] : 0;
+            __syncthreads();
+            s[tid] += v;
+            __syncthreads();
+        }
+        if (i < n) off[i] = s_carry + s[tid] - c;
+        atomicMax(&s_max, c);
+        __syncthreads();
+        if (tid == 0) s_carry += s[1023];
+        __syncthreads();
+    }
+    if (tid == 0) { off[n] = s_carry; total_max[0] = s_carry; total_max[1] = s_max; }
+}
+
+// gather the packed per-patch sample streams (SoA over the global sample index) — coalesced reads in k_unary
+__global__ void __launch_bounds__(256) k_patch_pack(int total, int Cp, int C, int wrows, int V, const int* __restrict__ idx,
+                                                    const float* __restrict__ sxf, const float* __restrict__ syf,
+                                                    const float* __restrict__ szf, const float* __restrict__ feat /*[C][V]*/,
+                                                    const float* __restrict__ wgt /*[wrows][V]*/, float* __restrict__ px,
+                                                    float* __restrict__ py, float* __restrict__ pz, float* __restrict__ pa /*[Cp][total]*/,
+                                                    float* __restrict__ pw) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total) return;
+    int i = idx[s];
+    px[s] = sxf[i]; py[s] = syf[i]; pz[s] = szf[i];
+    for (int c = 0; c < Cp; c++) {
+        float a = 0.f, w = 0.f;  // padded channels carry zero weight: they drop out of every weighted sum
+        if (c < C) {
+            a = feat[(size_t)c * V + i];
+            w = (c < wrows) ? wgt[(size_t)c * V + i] : 1.0f;  // src/DiscreteCostFunction.cpp:404-407,474-477
+        }
+        pa[(size_t)c * total + s] = a;
+        pw[(size_t)c * total + s] = w;
+    }
+}
+
+// face-packed target features: leaf -> (f[a][0..Cp), f[b][..], f[c][..]); univariate: float4 (fa, fb, fc, 0)
+__global__ void __launch_bounds__(256) k_face_pack(int F, int C, int Cp, int V, int univariate, const int* __restrict__ leaf_vid /*[F][3]*/,
+                                                   const float* __restrict__ feat /*[C][V]*/, float* __restrict__ out) {
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    int v0 = leaf_vid[3 * f], v1 = leaf_vid[3 * f + 1], v2 = leaf_vid[3 * f + 2];
+    if (univariate) {
+        float4 o = make_float4(feat[v0], feat[v1], feat[v2], 0.f);
+        reinterpret_cast<float4*>(out)[f] = o;
+    } else {
+        float* o = out + (size_t)f * 3 * Cp;
+        for (int c = 0; c < Cp; c++) {
+            o[c] = c < C ? feat[(size_t)c * V + v0] : 0.f;
+            o[Cp + c] = c < C ? feat[(size_t)c * V + v1] : 0.f;
+            o[2 * Cp + c] = c < C ? feat[(size_t)c * V + v2] : 0.f;
+        }
+    }
+}
+
+// =========================================================================================================
+// k_unary — the unary data term (src/DiscreteCostFunction.cpp:306-313,412-448,483-526; similarities.cc:122-173).
+// One CTA per (control point, label group).  Phase 1: stage the CP's patch (coalesced SoA streams) and the label
+// rotations in shared memory.  Phase 2: every thread takes (label, sample) items: rotate, locate on the target
+// icosphere by scalar four-way descent, gather ONE face-packed feature vector, interpolate.  Phase 3: one warp per
+// label reduces the weighted Pearson correlation (two-pass, fp64 accumulators, fixed order -> deterministic).
+// CQ = number of float4 channel quads (0 = univariate).
+// =========================================================================================================
+struct UnaryArgs {
+    int k_begin, Ns, L, G, Lg;          // shard rows, labels, label groups, labels per group
+    const int* off;                     // [Ns+1]
+    const float* px; const float* py; const float* pz; const float* pa; const float* pw;  // packed streams
+    int total;                          // stride of pa/pw channels
+    const float* Kf;                    // [N][L][9]
+    const double* cp;                   // [N][3] (hint base face)
+    const float* absw;                  // [N]
+    const float* face_feat;             // face-packed target features
+    IcoDev ico;
+    int simmeasure;
+    float* out;                         // [L][Ns]
+};
+
+template <int CQ>
+__global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
+    constexpr int CP_ = CQ == 0 ? 1 : 4 * CQ;  // padded channel count
+    extern __shared__ float smem[];
+    const int row = blockIdx.x / a.G, g = blockIdx.x - row * a.G;
+    const int k = a.k_begin + row;
+    const int l0 = g * a.Lg, l1 = min(a.L, l0 + a.Lg), nl = l1 - l0;
+    const int s0 = a.off[row], P = a.off[row + 1] - s0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // smem carve: xyz[3][P] | a[CP_][P] | w[CP_][P] | K[Lg][12] | tbuf[Lg][P]
+    float* sx = smem; float* sy = sx + P; float* sz = sy + P;
+    float* sa = sz + P; float* sw = sa + CP_ * P;
+    float* sK = sw + CP_ * P;
+    float* tb = sK + a.Lg * 12;
+    __shared__ int s_hint;
+
+    for (int i = tid; i < P; i += 256) {
+        sx[i] = a.px[s0 + i]; sy[i] = a.py[s0 + i]; sz[i] = a.pz[s0 + i];
+#pragma unroll
+        for (int c = 0; c < CP_; c++) {
+            sa[c * P + i] = a.pa[(size_t)c * a.total + s0 + i];
+            sw[c * P + i] = a.pw[(size_t)c * a.total + s0 + i];
+        }
+    }
+    for (int i = tid; i < nl * 9; i += 256) {
+        int l = i / 9, e = i - l * 9;
+        sK[l * 12 + e] = a.Kf[((size_t)k * a.L + l0 + l) * 9 + e];
+    }
+    if (tid == 0) s_hint = ico_base_face<float>((float)a.cp[3 * k], (float)a.cp[3 * k + 1], (float)a.cp[3 * k + 2]);
+    __syncthreads();
+    const int hint = s_hint;
+    const int items = nl * P;
+    const float invP = 1.0f / (float)max(P, 1);
+
+    for (int j = tid; j < items; j += 256) {
+        const int l = (int)(((float)j + 0.5f) * invP);
+        const int i = j - l * P;
+        const float x = sx[i], y = sy[i], z = sz[i];
+        const float* K = sK + l * 12;
+        // p' = p + (R - I) p : the small correction is computed at full relative precision
+        const float qx = x + (K[0] * x + K[1] * y + K[2] * z);
+        const float qy = y + (K[3] * x + K[4] * y + K[5] * z);
+        const float qz = z + (K[6] * x + K[7] * y + K[8] * z);
+        float al, be, ga;
+        const int leaf = ico_locate<float>(a.ico, hint, qx, qy, qz, al, be, ga);
+        const float inv = 1.0f / (al + be + ga);
+        if (CQ == 0) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(a.face_feat) + leaf);
+            tb[j] = (al * f.x + be * f.y + ga * f.z) * inv;
+        } else {
+            // multivariate: Pearson across the channels of this one sample (src/DiscreteCostFunction.cpp:515-518)
+            const float4* ff = reinterpret_cast<const float4*>(a.face_feat) + (size_t)leaf * 3 * CQ;
+            float t[CP_];
+            const float wa = al * inv, wb = be * inv, wc = ga * inv;
+#pragma unroll
+            for (int q = 0; q < CQ; q++) {
+                const float4 f0 = __ldg(ff + q), f1 = __ldg(ff + CQ + q), f2 = __ldg(ff + 2 * CQ + q);
+                t[4 * q + 0] = wa * f0.x + wb * f1.x + wc * f2.x;
+                t[4 * q + 1] = wa * f0.y + wb * f1.y + wc * f2.y;
+                t[4 * q + 2] = wa * f0.z + wb * f1.z + wc * f2.z;
+                t[4 * q + 3] = wa * f0.w + wb * f1.w + wc * f2.w;
+            }
+            float W = 0.f, Sa = 0.f, St = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP_; c++) {
+                const float w = sw[c * P + i];
+                W += w; Sa += w * sa[c * P + i]; St += w * t[c];
+            }
+            if (W > 0.f) { Sa /= W; St /= W; }
+            float pr = 0.f, va = 0.f, vt = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP_; c++) {
+                const float w = sw[c * P + i];
+                const float da = sa[c * P + i] - Sa, dt = t[c] - St;
+                pr += w * da * dt; va += w * da * da; vt += w * dt * dt;
+            }
+            if (W > 0.f) { pr /= W; va /= W; vt /= W; }
+            const float rho = (va == 0.f || vt == 0.f) ? 0.f : pr / (sqrtf(va) * sqrtf(vt));
+            tb[j] = 1.0f - (1.0f + rho) * 0.5f;
+        }
+    }
+    __syncthreads();
+
+    const float AW = a.absw[k];
+    const bool pos = (a.simmeasure == 1 || a.simmeasure == 2);
+    for (int l = warp; l < nl; l += 8) {
+        const float* t = tb + l * P;
+        double cost;
+        if (CQ == 0) {
+            double W = 0, Sa = 0, St = 0;
+            for (int i = lane; i < P; i += 32) {
+                const double w = sw[i];
+                W += w; Sa += w * (double)sa[i]; St += w * (double)t[i];
+            }
+            W = warp_sum(W); Sa = warp_sum(Sa); St = warp_sum(St);
+            if (W > 0) { Sa /= W; St /= W; }
+            double pr = 0, va = 0, vt = 0;
+            for (int i = lane; i < P; i += 32) {
+                const double w = sw[i];
+                const double da = (double)sa[i] - Sa, dt = (double)t[i] - St;
+                pr += w * da * dt; va += w * da * da; vt += w * dt * dt;
+            }
+            pr = warp_sum(pr); va = warp_sum(va); vt = warp_sum(vt);
+            if (W > 0) { pr /= W; va /= W; vt /= W; }
+            const double rho = (va == 0.0 || vt == 0.0) ? 0.0 : pr / (sqrt(va) * sqrt(vt));
+            cost = (double)AW * (1.0 - (1.0 + rho) * 0.5);
+        } else {
+            double s = 0;
+            for (int i = lane; i < P; i += 32) s += (double)t[i];
+            s = warp_sum(s);
+            if (P > 0) s /= (double)P;
+            cost = (double)AW * s;
+        }
+        if (!pos) cost = -cost;
+        if (lane == 0) a.out[(size_t)(l0 + l) * a.Ns + row] = (float)cost;
+    }
+}
+
+// =========================================================================================================
+// Triplet regulariser — computeTripletCost (src/DiscreteCostFunction.cpp:138-254), strain energy
+// (src/reg_tools.cpp:556-601,703-748, Gram form: SURVEY Appendix A), group variant
+// (src/DiscreteGroupCostFunction.cpp:9-30).  fp64: the cost is a difference of near-equal quantities for small
+// deformations and coordinates live at |x|~100.
+// =========================================================================================================
+struct TripGeom {            // per-triplet constants
+    double n[3];             // (v1-v0)x(v2-v0) of the CURRENT control triangle (fold test)
+    double G11, G12, G22;    // Gram of the ORIGINAL triangle
+    double det0;
+    double oang[3], oarea;   // rmode 2
+};
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__device__ __forceinline__ void tri_angles(const double* v0, const double* v1, const double* v2, double* ang) {
+    const double* v[3] = {v0, v1, v2};
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double e1[3], e2[3];
+        for (int j = 0; j < 3; j++) { e1[j] = v[(i + 1) % 3][j] - v[i][j]; e2[j] = v[(i + 2) % 3][j] - v[i][j]; }
+        double c = dot3(e1, e2) / (sqrt(dot3(e1, e1)) * sqrt(dot3(e2, e2)));
+        c = fmin(1.0, fmax(-1.0, c));
+        ang[i] = acos(c);
+    }
+}
+
+__device__ __forceinline__ void trip_geom(const DevParams& p, const double* v0, const double* v1, const double* v2, const double* o0,
+                                          const double* o1, const double* o2, TripGeom& g) {
+    double e1[3], e2[3];
+    for (int j = 0; j < 3; j++) { e1[j] = v1[j] - v0[j]; e2[j] = v2[j] - v0[j]; }
+    cross3(e1, e2, g.n);
+    double E1[3], E2[3];
+    for (int j = 0; j < 3; j++) { E1[j] = o1[j] - o0[j]; E2[j] = o2[j] - o0[j]; }
+    g.G11 = dot3(E1, E1); g.G12 = dot3(E1, E2); g.G22 = dot3(E2, E2);
+    g.det0 = g.G11 * g.G22 - g.G12 * g.G12;
+    if (p.rmode == 2 && !p.group) {
+        tri_angles(o0, o1, o2, g.oang);
+        double c[3]; cross3(E1, E2, c);
+        g.oarea = 0.5 * sqrt(dot3(c, c));
+    }
+}
+
+// strain energy from Gram entries; k_exp == 2 avoids sqrt/pow: R^2+R^-2-2 = I1*^2-4, J^2 = I3
+__device__ __forceinline__ double strain_energy(double g11, double g12, double g22, const TripGeom& g, double mu, double kappa, double k_exp) {
+    const double trC = (g11 * g.G22 - 2.0 * g12 * g.G12 + g22 * g.G11) / g.det0;
+    const double I3 = (g11 * g22 - g12 * g12) / g.det0;
+    if (k_exp == 2.0) {
+        const double r = 1.0 / I3;
+        const double i1s2 = trC * trC * r;  // (I1*)^2
+        // reference: R = 1 if I1* <= 2 (J = sqrt(I3) > 0 so the sign of I1* is the sign of trC > 0)
+        const double shear = (i1s2 <= 4.0) ? 0.0 : (i1s2 - 4.0) + 0.0;
+        // R^2 + R^-2 - 2 with R = (I1* + sqrt(I1*^2-4))/2 :  R + 1/R = I1*  =>  R^2 + R^-2 = I1*^2 - 2
+        return 0.5 * (mu * shear + kappa * (I3 + r - 2.0));
+    }
+    const double J = sqrt(I3);
+    const double I1s = trC / J;
+    const double R = (I1s <= 2.0) ? 1.0 : 0.5 * (I1s + sqrt(I1s * I1s - 4.0));
+    const double Rs = pow(R, k_exp), Js = pow(J, k_exp);
+    return 0.5 * (mu * (Rs + 1.0 / Rs - 2.0) + kappa * (Js + 1.0 / Js - 2.0));
+}
+
+__device__ __forceinline__ double trip_cost(const DevParams& p, const TripGeom& g, const double* d0, const double* d1, const double* d2) {
+    double e1[3], e2[3], nn[3];
+    for (int j = 0; j < 3; j++) { e1[j] = d1[j] - d0[j]; e2[j] = d2[j] - d0[j]; }
+    cross3(e1, e2, nn);
+    const bool fold = dot3(nn, g.n) < 0.0;  // sign of the dot of the unit normals (:163)
+    if (p.group) {                           // src/DiscreteGroupCostFunction.cpp:23,29
+        if (fold) return 1e7;
+        const double W = strain_energy(dot3(e1, e1), dot3(e1, e2), dot3(e2, e2), g, p.mu, p.kappa, 2.0);
+        return p.lambda * pow(W, p.rexp);
+    }
+    double cost, weight = 1.0;
+    if (fold) { cost = 1.0; weight += 1e6; }
+    else if (p.rmode == 3) cost = strain_energy(dot3(e1, e1), dot3(e1, e2), dot3(e2, e2), g, p.mu, p.kappa, p.k_exp);
+    else {  // rmode 2 (:172-192)
+        double ang[3];
+        tri_angles(d0, d1, d2, ang);
+        const double area = 0.5 * sqrt(dot3(nn, nn));
+        const double distortion = log2(area / g.oarea);
+        double tweight = 1.0;
+        if (p.dweight && distortion != 1.0) tweight = exp(fabs(distortion - 1.0));
+        double diff = 0.0;
+        for (int i = 0; i < 3; i++) { const double dd = ang[i] - g.oang[i]; diff += dd * dd; }
+        cost = tweight * sqrt(diff);
+        if (p.anorm) weight *= (1.0 / p.meanangle);
+    }
+    if (fabs(cost) < 1e-8) cost = 0.0;                                      // :246
+    const double pw = (p.rexp == 2.0) ? cost * cost : pow(cost, p.rexp);     // :253
+    return weight * p.lambda * pw;
+}
+
+struct TripArgs {
+    DevParams p;
+    int L;
+    int group_N, group_T;            // per-subject sizes (group mode)
+    const int* trip;                 // [T][3]
+    const double* cp;                // [N][3] current
+    const double* orig;              // [N or N_subj][3]
+    const double* disp;              // [N][L][3]
+};
+
+__device__ __forceinline__ void trip_load(const TripArgs& a, int t, int id[3], TripGeom& g) {
+    id[0] = a.trip[3 * t]; id[1] = a.trip[3 * t + 1]; id[2] = a.trip[3 * t + 2];
+    int m[3] = {id[0], id[1], id[2]};
+    if (a.p.group) {
+        const int mesh = t / a.group_T;
+        for (int j = 0; j < 3; j++) m[j] = id[j] - mesh * a.group_N;
+    }
+    trip_geom(a.p, a.cp + 3 * id[0], a.cp + 3 * id[1], a.cp + 3 * id[2], a.orig + 3 * m[0], a.orig + 3 * m[1], a.orig + 3 * m[2], g);
+}
+
+// arbitrary queries (t, la, lb, lc)
+__global__ void __launch_bounds__(128) k_triplet_queries(TripArgs a, int n, const int* __restrict__ q, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = q[4 * i];
+    int id[3]; TripGeom g;
+    trip_load(a, t, id, g);
+    out[i] = trip_cost(a.p, g, a.disp + ((size_t)id[0] * a.L + q[4 * i + 1]) * 3, a.disp + ((size_t)id[1] * a.L + q[4 * i + 2]) * 3,
+                       a.disp + ((size_t)id[2] * a.L + q[4 * i + 3]) * 3);
+}
+
+// fusion-move costs (include/Fusion/Fusion.h:187-194): combo bit2->A, bit1->B, bit0->C take label alpha.
+// alpha >= 0: out[t][8]; alpha < 0: all labels, out[alpha][t][8].
+template <typename OutT>
+__global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const int* __restrict__ labeling, int alpha, OutT* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nalpha = alpha < 0 ? a.L : 1;
+    if (gid >= (long long)nalpha * T * 8) return;
+    const int combo = (int)(gid & 7);
+    const long long rest = gid >> 3;
+    const int t = (int)(rest % T);
+    const int al = alpha < 0 ? (int)(rest / T) : alpha;
+    int id[3]; TripGeom g;
+    trip_load(a, t, id, g);
+    const int la = (combo & 4) ? al : labeling[id[0]];
+    const int lb = (combo & 2) ? al : labeling[id[1]];
+    const int lc = (combo & 1) ? al : labeling[id[2]];
+    out[gid] = (OutT)trip_cost(a.p, g, a.disp + ((size_t)id[0] * a.L + la) * 3, a.disp + ((size_t)id[1] * a.L + lb) * 3,
+                               a.disp + ((size_t)id[2] * a.L + lc) * 3);
+}
+
+// full table: one CTA per triplet; displaced corners staged in shared memory; thread = (la,lb), loop lc;
+// results staged in shared memory and written with coalesced stores (the table is store-bound: 4 B/eval).
+__global__ void __launch_bounds__(256) k_triplet_table(TripArgs a, int t0, float* __restrict__ out) {
+    extern __shared__ double sm_d[];
+    const int L = a.L, L2 = L * L, L3 = L2 * L;
+    double* sd = sm_d;                                   // [3][L][3]
+    float* sres = reinterpret_cast<float*>(sd + 9 * L);  // [L3]
+    __shared__ TripGeom g;
+    __shared__ int id[3];
+    const int t = t0 + blockIdx.x;
+    if (threadIdx.x == 0) trip_load(a, t, id, g);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * L; i += blockDim.x) {
+        int v = i / (3 * L), r = i - v * 3 * L;
+        sd[i] = a.disp[(size_t)id[v] * L * 3 + r];
+    }
+    __syncthreads();
+    for (int ab = threadIdx.x; ab < L2; ab += blockDim.x) {
+        const int la = ab / L, lb = ab - la * L;
+        const double* d0 = sd + 3 * la;
+        const double* d1 = sd + 3 * L + 3 * lb;
+        for (int lc = 0; lc < L; lc++) sres[ab * L + lc] = (float)trip_cost(a.p, g, d0, d1, sd + 6 * L + 3 * lc);
+    }
+    __syncthreads();
+    float* o = out + (size_t)blockIdx.x * L3;
+    for (int i = threadIdx.x; i < L3; i += blockDim.x) o[i] = sres[i];
+}
+
+// =========================================================================================================
+// Pairwise rotation regulariser — computePairwiseCost (src/DiscreteCostFunction.cpp:256-296), table layout :303.
+// =========================================================================================================
+struct PairArgs {
+    DevParams p;
+    int L, P;
+    const int* pairs;      // [P][2]
+    const double* Kd;      // [N][L][9]  R - I
+    const double* disp;    // [N][L][3]
+    const double* cp;      // current CP grid
+    const double* ocp;     // _oCPgrid
+    const int* tris;       // [T][3] CP-grid faces
+    const int* vt_off; const int* vt_idx;  // vertex -> incident faces (ascending)
+};
+
+__device__ __forceinline__ double pair_cost(const PairArgs& a, int pr, int la, int lb) {
+    const int va = a.pairs[2 * pr], vb = a.pairs[2 * pr + 1];
+    const double* K1 = a.Kd + ((size_t)va * a.L + la) * 9;
+    const double* K2 = a.Kd + ((size_t)vb * a.L + lb) * 9;
+    double fro = 0.0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) fro += K1[i] * K2[i];
+    // (trace(R1^T R2) - 1)/2 = 1 + (tr K1 + tr K2 + K1:K2)/2
+    const double x = -0.5 * ((K1[0] + K1[4] + K1[8]) + (K2[0] + K2[4] + K2[8]) + fro);  // = 1 - (tr-1)/2
+    if (!(fabs(x) > kEPSILON)) return 0.0;                                            // :272
+    const double theta = (x < 0.5) ? 2.0 * asin(sqrt(fmax(x, 0.0) * 0.5)) : acos(1.0 - x);
+    const double theta_MVD = 2.0 * asin(a.p.mvdmax / (2.0 * kRAD));                   // :262
+    double weight = 1.0;
+    const double* da = a.disp + ((size_t)va * a.L + la) * 3;
+    const double* db = a.disp + ((size_t)vb * a.L + lb) * 3;
+    for (int e = a.vt_off[va]; e < a.vt_off[va + 1]; e++) {  // :274-282 faces incident to the FIRST vertex
+        const int f = a.vt_idx[e];
+        const double* o[3]; const double* c[3];
+        for (int j = 0; j < 3; j++) {
+            const int v = a.tris[3 * f + j];
+            o[j] = a.ocp + 3 * v;
+            c[j] = (v == va) ? da : (v == vb) ? db : a.cp + 3 * v;
+        }
+        double e1[3], e2[3], n0[3], n1[3];
+        for (int j = 0; j < 3; j++) { e1[j] = o[1][j] - o[0][j]; e2[j] = o[2][j] - o[0][j]; }
+        cross3(e1, e2, n0);
+        for (int j = 0; j < 3; j++) { e1[j] = c[1][j] - c[0][j]; e2[j] = c[2][j] - c[0][j]; }
+        cross3(e1, e2, n1);
+        if (dot3(n0, n1) < 0.0) { weight += 1e6; break; }
+    }
+    const double cost = (1.4142135623730951 * theta) / theta_MVD;  // :284
+    if (a.p.rexp == 1.0) return weight * a.p.lambda * cost;        // :286-289
+    return weight * a.p.lambda * pow(cost, a.p.rexp);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(128) k_pair_table(PairArgs a, OutT* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int L2 = a.L * a.L;
+    if (gid >= (long long)a.P * L2) return;
+    const int pr = (int)(gid / L2);
+    const int r = (int)(gid - (long long)pr * L2);
+    const int lb = r / a.L, la = r - lb * a.L;  // paircosts[p*L*L + labelB*L + labelA]
+    out[gid] = (OutT)pair_cost(a, pr, la, lb);
+}
+
+__global__ void __launch_bounds__(128) k_pair_queries(PairArgs a, int n, const int* __restrict__ q, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = pair_cost(a, q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+}
+
+// =========================================================================================================
+// k_locate — stand-alone point location + barycentric weights (msm_locate), fp64.
+// =========================================================================================================
+__global__ void __launch_bounds__(256) k_locate(IcoDev ico, int M, const double* __restrict__ pts, const int* __restrict__ leaf_user /*[F]*/,
+                                                const unsigned char* __restrict__ leaf_perm /*[F][3]*/, int* __restrict__ tri,
+                                                double* __restrict__ w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    double al, be, ga;
+    const double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    const int hint = ico_base_face<double>(px, py, pz);
+    const int leaf = ico_locate<double>(ico, hint, px, py, pz, al, be, ga);
+    const double inv = 1.0 / (al + be + ga);
+    const double wl[3] = {al * inv, be * inv, ga * inv};
+    tri[i] = leaf_user[leaf];
+    // leaf corner j sits at position leaf_perm[leaf][j] of the caller's triangle
+    w[3 * i + leaf_perm[3 * leaf + 0]] = wl[0];
+    w[3 * i + leaf_perm[3 * leaf + 1]] = wl[1];
+    w[3 * i + leaf_perm[3 * leaf + 2]] = wl[2];
+}
+
+}  // namespace msm

@@ -1,0 +1,126 @@
+// locate.cuh — device-side spherical point location on a regular icosphere (north_star kernel (c)).
+// Replaces newresampler::Octree::get_closest_triangle + barycentric_weight ([EXT] A3/A4; call sites
+// src/DiscreteCostFunction.cpp:421-433,492-505).  See ico_hierarchy.h for the derivation.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace msm {
+
+struct IcoDev {
+    int depth;
+    int nleaf_per_base;          // 4^depth
+    int leaf_off;                // (4^depth - 1)/3 : heap index of the first leaf-level node
+    const float4* ntab;          // [nodes] (n_ab, n_bc, n_ca, -)
+    const double4* ntab_d;       // same in fp64 (msm_locate, precise paths)
+};
+
+// 20 base faces: dual basis rows (alpha = A.p, beta = B.p, gamma = C.p) and centre directions.
+struct IcoBase {
+    float dual[20][9];
+    float centre[20][3];
+    double dual_d[20][9];
+    double centre_d[20][3];
+};
+__constant__ IcoBase c_ico_base;
+
+template <typename T> struct NodeN;
+template <> struct NodeN<float> {
+    static __device__ __forceinline__ void load(const IcoDev& ico, int n, float& nab, float& nbc, float& nca) {
+        float4 v = __ldg(ico.ntab + n);
+        nab = v.x; nbc = v.y; nca = v.z;
+    }
+};
+template <> struct NodeN<double> {
+    static __device__ __forceinline__ void load(const IcoDev& ico, int n, double& nab, double& nbc, double& nca) {
+        double4 v = ico.ntab_d[n];
+        nab = v.x; nbc = v.y; nca = v.z;
+    }
+};
+
+template <typename T> __device__ __forceinline__ const T* base_dual(int b);
+template <> __device__ __forceinline__ const float* base_dual<float>(int b) { return c_ico_base.dual[b]; }
+template <> __device__ __forceinline__ const double* base_dual<double>(int b) { return c_ico_base.dual_d[b]; }
+template <typename T> __device__ __forceinline__ const T* base_centre(int b);
+template <> __device__ __forceinline__ const float* base_centre<float>(int b) { return c_ico_base.centre[b]; }
+template <> __device__ __forceinline__ const double* base_centre<double>(int b) { return c_ico_base.centre_d[b]; }
+
+// Base face containing p: the face cones of a regular icosahedron are the Voronoi cells of the face centres.
+template <typename T>
+__device__ __forceinline__ int ico_base_face(T px, T py, T pz) {
+    int best = 0;
+    T bv = -1e30f;
+#pragma unroll
+    for (int b = 0; b < 20; b++) {
+        const T* c = base_centre<T>(b);
+        T v = px * c[0] + py * c[1] + pz * c[2];
+        if (v > bv) { bv = v; best = b; }
+    }
+    return best;
+}
+
+// Four-way descent.  In: coordinates (al,be,ga) of p in the corner basis of base face `base`.
+// Out: canonical leaf index, and (al,be,ga) in the leaf's corner basis (un-normalised barycentric weights).
+template <typename T>
+__device__ __forceinline__ int ico_descend(const IcoDev& ico, int base, T& al, T& be, T& ga) {
+    int n = 0;
+    for (int l = 0; l < ico.depth; l++) {
+        T nab, nbc, nca;
+        NodeN<T>::load(ico, n, nab, nbc, nca);
+        const T s = al + be + ga;
+        const T sa = (al + al) - s, sb = (be + be) - s, sc = (ga + ga) - s;  // alpha-beta-gamma etc.
+        int child;
+        T x, y, z;
+        if (sa > T(0)) { child = 0; x = sa;       y = be * nab; z = ga * nca; }
+        else if (sb > T(0)) { child = 1; x = al * nab; y = sb;       z = ga * nbc; }
+        else if (sc > T(0)) { child = 2; x = al * nca; y = be * nbc; z = sc; }
+        else { child = 3; x = -sa * nbc; y = -sb * nca; z = -sc * nab; }
+        al = x; be = y; ga = z;
+        n = 4 * n + 1 + child;
+    }
+    return base * ico.nleaf_per_base + (n - ico.leaf_off);
+}
+
+// Full location: hint base face first (all samples of one control point's patch almost always share it).
+template <typename T>
+__device__ __forceinline__ int ico_locate(const IcoDev& ico, int hint_base, T px, T py, T pz, T& al, T& be, T& ga) {
+    int base = hint_base;
+    const T* d = base_dual<T>(base);
+    al = d[0] * px + d[1] * py + d[2] * pz;
+    be = d[3] * px + d[4] * py + d[5] * pz;
+    ga = d[6] * px + d[7] * py + d[8] * pz;
+    if (fminf(float(al), fminf(float(be), float(ga))) < 0.f) {
+        base = ico_base_face<T>(px, py, pz);
+        d = base_dual<T>(base);
+        al = d[0] * px + d[1] * py + d[2] * pz;
+        be = d[3] * px + d[4] * py + d[5] * pz;
+        ga = d[6] * px + d[7] * py + d[8] * pz;
+        // rounding at a cone boundary can leave a tiny negative coordinate: clamp (weights stay continuous)
+        al = al < T(0) ? T(0) : al; be = be < T(0) ? T(0) : be; ga = ga < T(0) ? T(0) : ga;
+    }
+    return ico_descend<T>(ico, base, al, be, ga);
+}
+
+// Minimal (Rodrigues) rotation taking direction a onto direction b, returned as K = R - I, fp64.
+// Restates estimate_rotation_matrix ([EXT] A2): identity below 1e-8 rad.
+__device__ __forceinline__ void rodrigues_minus_identity(const double a_[3], const double b_[3], double K[9]) {
+    double na = rsqrt(a_[0] * a_[0] + a_[1] * a_[1] + a_[2] * a_[2]);
+    double nb = rsqrt(b_[0] * b_[0] + b_[1] * b_[1] + b_[2] * b_[2]);
+    double a[3] = {a_[0] * na, a_[1] * na, a_[2] * na}, b[3] = {b_[0] * nb, b_[1] * nb, b_[2] * nb};
+    double c = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    c = fmin(1.0, fmax(-1.0, c));
+    double k[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    double s = sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);  // sin(theta), well conditioned for small theta
+    double theta = atan2(s, c);
+#pragma unroll
+    for (int i = 0; i < 9; i++) K[i] = 0.0;
+    if (fabs(theta) < 1e-8 || s == 0.0) return;
+    double kx = k[0] / s, ky = k[1] / s, kz = k[2] / s;
+    // 1 - cos(theta) = s^2 / (1 + c) avoids cancellation for small angles
+    double omc = (c > 0.0) ? s * s / (1.0 + c) : 1.0 - c;
+    // K = s*[k]x + omc*[k]x^2 ; [k]x^2 = k k^T - I
+    K[0] = omc * (kx * kx - 1.0);      K[1] = -s * kz + omc * kx * ky;   K[2] = s * ky + omc * kx * kz;
+    K[3] = s * kz + omc * kx * ky;     K[4] = omc * (ky * ky - 1.0);     K[5] = -s * kx + omc * ky * kz;
+    K[6] = -s * ky + omc * kx * kz;    K[7] = s * kx + omc * ky * kz;    K[8] = omc * (kz * kz - 1.0);
+}
+
+}  // namespace msm

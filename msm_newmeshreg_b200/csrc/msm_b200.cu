@@ -1,0 +1,856 @@
+// msm_b200.cu — context + extern "C" layer (include/msm_b200.h) over the sm_100a kernels in kernels.cuh.
+// Host code is C++; there is no CPU fallback: every compute entry point launches CUDA kernels or fails.
+#include "../../include/msm_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "ico_hierarchy.h"
+#include "kernels.cuh"
+
+using namespace msm;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + 256);
+        if (e == cudaSuccess) cap = bytes + 256;
+        return e;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct msm_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    bool timing = false;
+    std::map<std::string, float> last_ms;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    msm_params par;
+
+    // target
+    IcoHierarchy ico;
+    bool have_target = false;
+    int Vt = 0, Ft = 0, Ct = 0;
+    DevBuf d_ntab, d_ntab_d, d_leaf_vid, d_leaf_user, d_leaf_perm, d_tfeat, d_face_feat;
+    int face_feat_cq = -1;  // layout the face-packed features were built for (-1 none, 0 univariate, q quads)
+
+    // source
+    int Vs = 0, Cs = 0, wrows = 0;
+    bool multivariate = false;
+    std::vector<double> h_src;
+    DevBuf d_src, d_sxf, d_syf, d_szf, d_sfeat, d_swgt;
+
+    // control-point grid
+    int N = 0, Tcp = 0;
+    std::vector<double> h_cp, h_maxsep;
+    DevBuf d_cp, d_ocp, d_orig, d_maxsep, d_absw, d_tris, d_vt_off, d_vt_idx;
+    int k_begin = 0, k_end = 0;
+
+    // labels
+    int L = 0;
+    double centre[3] = {0, 0, 0};
+    DevBuf d_labels, d_disp, d_Kf, d_Kd;
+    bool rot_dirty = true;
+
+    // cliques
+    int P = 0, Tn = 0;
+    DevBuf d_pairs, d_trip;
+    int S = 1, N_subj = 0, T_subj = 0;
+
+    // patches
+    bool have_patches = false;
+    long long total = 0;
+    int maxP = 0;
+    DevBuf d_counts, d_off, d_idx, d_unc, d_unc_count, d_acc_off, d_acc_idx, d_totmax;
+    DevBuf d_px, d_py, d_pz, d_pa, d_pw;
+    int pack_cp = 0;
+
+    // outputs / scratch
+    DevBuf d_unary, d_scratch, d_scratch2;
+    PinBuf h_pin;
+    std::vector<double> h_unary;  // last unary table [L][N] (shard rows) for msm_total_cost
+    bool have_unary = false;
+};
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+            return 1;                                                                                  \
+        }                                                                                              \
+    } while (0)
+#define FAIL(msg)          \
+    do {                   \
+        ctx->err = (msg);  \
+        return 1;          \
+    } while (0)
+#define KLAUNCH_CHECK()                     \
+    do {                                    \
+        ctx->launches++;                    \
+        CK(cudaGetLastError());             \
+    } while (0)
+
+namespace {
+
+struct Timer {
+    msm_ctx* ctx; const char* name;
+    Timer(msm_ctx* c, const char* n) : ctx(c), name(n) { if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream); }
+    ~Timer() {
+        if (ctx->timing) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            cudaEventSynchronize(ctx->ev1);
+            float ms = -1.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            ctx->last_ms[name] = ms;
+        }
+    }
+};
+
+DevParams dev_params(const msm_ctx* ctx) {
+    DevParams d;
+    const msm_params& p = ctx->par;
+    d.lambda = p.lambda; d.rexp = p.rexp; d.mu = p.mu; d.kappa = p.kappa; d.k_exp = p.k_exp; d.range = p.range;
+    d.meanangle = p.meanangle; d.mvdmax = p.mvdmax; d.simmeasure = p.simmeasure; d.rmode = p.rmode; d.dweight = p.dweight;
+    d.anorm = p.anorm; d.group = p.group;
+    return d;
+}
+
+template <typename T>
+int upload(msm_ctx* ctx, DevBuf& b, const T* h, size_t n) {
+    CK(b.ensure(std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CK(cudaMemcpyAsync(b.p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int upload_xyz_soa_f(msm_ctx* ctx, const double* xyz, int n, DevBuf& bx, DevBuf& by, DevBuf& bz) {
+    CK(ctx->h_pin.ensure((size_t)n * 3 * sizeof(float)));
+    float* f = ctx->h_pin.as<float>();
+    for (int i = 0; i < n; i++) { f[i] = (float)xyz[3 * i]; f[n + i] = (float)xyz[3 * i + 1]; f[2 * n + i] = (float)xyz[3 * i + 2]; }
+    CK(bx.ensure((size_t)n * 4)); CK(by.ensure((size_t)n * 4)); CK(bz.ensure((size_t)n * 4));
+    CK(cudaMemcpyAsync(bx.p, f, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(by.p, f + n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(bz.p, f + 2 * n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // pinned staging buffer is reused
+    return 0;
+}
+
+int upload_as_float(msm_ctx* ctx, DevBuf& b, const double* h, size_t n) {
+    CK(ctx->h_pin.ensure(n * sizeof(float)));
+    float* f = ctx->h_pin.as<float>();
+    for (size_t i = 0; i < n; i++) f[i] = (float)h[i];
+    CK(b.ensure(std::max<size_t>(n, 1) * 4));
+    CK(cudaMemcpyAsync(b.p, f, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+IcoDev ico_dev(const msm_ctx* ctx) {
+    IcoDev d;
+    d.depth = ctx->ico.depth;
+    d.nleaf_per_base = 1 << (2 * ctx->ico.depth);
+    d.leaf_off = (d.nleaf_per_base - 1) / 3;
+    d.ntab = ctx->d_ntab.as<float4>();
+    d.ntab_d = ctx->d_ntab_d.as<double4>();
+    return d;
+}
+
+int ensure_label_rot(msm_ctx* ctx) {
+    if (!ctx->rot_dirty) return 0;
+    if (ctx->N <= 0 || ctx->L <= 0) FAIL("set_cpgrid and set_labels must be called first");
+    const size_t nl = (size_t)ctx->N * ctx->L;
+    CK(ctx->d_disp.ensure(nl * 3 * sizeof(double)));
+    CK(ctx->d_Kf.ensure(nl * 9 * sizeof(float)));
+    CK(ctx->d_Kd.ensure(nl * 9 * sizeof(double)));
+    Timer t(ctx, "label_rot");
+    k_label_rot<<<(unsigned)((nl + 255) / 256), 256, 0, ctx->stream>>>(ctx->N, ctx->L, ctx->d_cp.as<double>(), ctx->d_labels.as<double>(),
+                                                                      ctx->centre[0], ctx->centre[1], ctx->centre[2],
+                                                                      ctx->d_disp.as<double>(), ctx->d_Kf.as<float>(), ctx->d_Kd.as<double>());
+    KLAUNCH_CHECK();
+    ctx->rot_dirty = false;
+    return 0;
+}
+
+int ensure_face_feat(msm_ctx* ctx) {
+    if (!ctx->have_target || ctx->Ct <= 0) FAIL("target features not set");
+    const int want = ctx->multivariate ? (ctx->Ct + 3) / 4 : 0;
+    if (!ctx->multivariate && ctx->Ct != 1) FAIL("univariate cost function needs C == 1");
+    if (ctx->face_feat_cq == want) return 0;
+    if (want > 4) FAIL("multivariate cost function supports at most 16 channels in this build");
+    const int Cp = want == 0 ? 1 : 4 * want;
+    const size_t per_face = want == 0 ? 4 : (size_t)3 * Cp;
+    CK(ctx->d_face_feat.ensure((size_t)ctx->Ft * per_face * sizeof(float)));
+    k_face_pack<<<(ctx->Ft + 255) / 256, 256, 0, ctx->stream>>>(ctx->Ft, ctx->Ct, Cp, ctx->Vt, want == 0 ? 1 : 0, ctx->d_leaf_vid.as<int>(),
+                                                               ctx->d_tfeat.as<float>(), ctx->d_face_feat.as<float>());
+    KLAUNCH_CHECK();
+    ctx->face_feat_cq = want;
+    return 0;
+}
+
+TripArgs trip_args(msm_ctx* ctx) {
+    TripArgs a;
+    a.p = dev_params(ctx);
+    a.L = ctx->L;
+    a.group_N = ctx->N_subj; a.group_T = ctx->T_subj;
+    a.trip = ctx->d_trip.as<int>();
+    a.cp = ctx->d_cp.as<double>();
+    a.orig = ctx->d_orig.as<double>();
+    a.disp = ctx->d_disp.as<double>();
+    return a;
+}
+
+int check_triplets(msm_ctx* ctx) {
+    if (ctx->Tn <= 0) FAIL("set_triplets must be called first");
+    if (ctx->par.group) {
+        if (ctx->N_subj <= 0 || ctx->T_subj <= 0) FAIL("group mode needs msm_set_group");
+    } else if (ctx->par.rmode != 2 && ctx->par.rmode != 3) {
+        FAIL("DiscreteModel computeTripletCost regoption does not exist");  // src/DiscreteCostFunction.cpp:242
+    }
+    return ensure_label_rot(ctx);
+}
+
+PairArgs pair_args(msm_ctx* ctx) {
+    PairArgs a;
+    a.p = dev_params(ctx);
+    a.L = ctx->L; a.P = ctx->P;
+    a.pairs = ctx->d_pairs.as<int>();
+    a.Kd = ctx->d_Kd.as<double>();
+    a.disp = ctx->d_disp.as<double>();
+    a.cp = ctx->d_cp.as<double>();
+    a.ocp = ctx->d_ocp.as<double>();
+    a.tris = ctx->d_tris.as<int>();
+    a.vt_off = ctx->d_vt_off.as<int>();
+    a.vt_idx = ctx->d_vt_idx.as<int>();
+    return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+void msm_default_params(msm_params* p) {
+    p->lambda = 1.0; p->rexp = 2.0; p->mu = 0.4f; p->kappa = 1.6f; p->k_exp = 2.0; p->range = 1.0;
+    p->simmeasure = 2; p->rmode = 1; p->dweight = 0; p->anorm = 0; p->meanangle = 0.0; p->mvdmax = 0.0; p->group = 0;
+    p->bary_orthogonal = 0;
+}
+
+int msm_create(int device, msm_ctx** out) {
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+        return 1;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return 1; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return 1; }
+    msm_ctx* ctx = new msm_ctx();
+    ctx->device = device;
+    msm_default_params(&ctx->par);
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete ctx;
+        return 1;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return 0;
+}
+
+void msm_destroy(msm_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* msm_last_error(const msm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int msm_set_stream(msm_ctx* ctx, void* s) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return 0;
+}
+int msm_synchronize(msm_ctx* ctx) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+int msm_set_params(msm_ctx* ctx, const msm_params* p) {
+    if (p->bary_orthogonal) FAIL("bary_orthogonal: only the radial projection (A4 default) is implemented on the device");
+    ctx->par = *p;
+    return 0;
+}
+
+int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int F, const double* feat, int C) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_target = false;
+    ctx->face_feat_cq = -1;
+    if (!ctx->ico.build(xyz, V, tris, F)) FAIL("msm_set_target: " + ctx->ico.error);
+    const IcoHierarchy& H = ctx->ico;
+    ctx->Vt = V; ctx->Ft = F; ctx->Ct = feat ? C : 0;
+    // node tables
+    {
+        size_t nn = std::max<size_t>(H.ntab.size(), 1);
+        std::vector<float> nf(nn * 4, 0.f);
+        std::vector<double> nd(nn * 4, 0.0);
+        for (size_t i = 0; i < H.ntab.size(); i++)
+            for (int j = 0; j < 3; j++) { nf[4 * i + j] = (float)H.ntab[i][j]; nd[4 * i + j] = H.ntab[i][j]; }
+        if (upload(ctx, ctx->d_ntab, nf.data(), nf.size())) return 1;
+        if (upload(ctx, ctx->d_ntab_d, nd.data(), nd.size())) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    {
+        static IcoBase hb;  // ~3.4 KB
+        for (int b = 0; b < 20; b++) {
+            for (int j = 0; j < 9; j++) { hb.dual[b][j] = (float)H.dual[b][j]; hb.dual_d[b][j] = H.dual[b][j]; }
+            for (int j = 0; j < 3; j++) { hb.centre[b][j] = (float)H.centre[b][j]; hb.centre_d[b][j] = H.centre[b][j]; }
+        }
+        CK(cudaMemcpyToSymbol(c_ico_base, &hb, sizeof(IcoBase)));
+    }
+    {
+        std::vector<int> lv((size_t)F * 3);
+        std::vector<unsigned char> perm((size_t)F * 3);
+        for (int f = 0; f < F; f++) {
+            const int uf = H.leaf_user_face[f];
+            for (int j = 0; j < 3; j++) {
+                lv[3 * f + j] = H.leaf_vid[f][j];
+                int pos = 0;
+                for (int q = 0; q < 3; q++) if (tris[3 * uf + q] == H.leaf_vid[f][j]) pos = q;
+                perm[3 * f + j] = (unsigned char)pos;
+            }
+        }
+        if (upload(ctx, ctx->d_leaf_vid, lv.data(), lv.size())) return 1;
+        if (upload(ctx, ctx->d_leaf_user, H.leaf_user_face.data(), H.leaf_user_face.size())) return 1;
+        if (upload(ctx, ctx->d_leaf_perm, perm.data(), perm.size())) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (feat) {
+        if (C <= 0) FAIL("msm_set_target: C must be positive");
+        if (upload_as_float(ctx, ctx->d_tfeat, feat, (size_t)C * V)) return 1;
+    }
+    ctx->have_target = true;
+    return 0;
+}
+
+int msm_set_source(msm_ctx* ctx, const double* xyz, int V, const double* feat, int C, const double* cfweight, int wrows, int multivariate) {
+    CK(cudaSetDevice(ctx->device));
+    if (V <= 0 || C <= 0) FAIL("CostFunction::You must supply source and target meshes.");  // src/DiscreteCostFunction.cpp:112-113
+    if (wrows != 0 && wrows != 1 && wrows != C)
+        FAIL("DiscreteModel ERROR:: costfunction weighting has dimensions incompatible with data");  // :116-117
+    ctx->Vs = V; ctx->Cs = C; ctx->wrows = wrows; ctx->multivariate = multivariate != 0;
+    if (upload_as_float(ctx, ctx->d_sfeat, feat, (size_t)C * V)) return 1;
+    if (wrows > 0 && upload_as_float(ctx, ctx->d_swgt, cfweight, (size_t)wrows * V)) return 1;
+    ctx->have_patches = false;
+    return msm_reset_source(ctx, xyz);
+}
+
+int msm_reset_source(msm_ctx* ctx, const double* xyz) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->Vs <= 0) FAIL("msm_set_source must be called first");
+    ctx->h_src.assign(xyz, xyz + (size_t)ctx->Vs * 3);
+    if (upload(ctx, ctx->d_src, xyz, (size_t)ctx->Vs * 3)) return 1;
+    if (upload_xyz_soa_f(ctx, xyz, ctx->Vs, ctx->d_sxf, ctx->d_syf, ctx->d_szf)) return 1;
+    ctx->have_patches = false;
+    return 0;
+}
+
+int msm_set_cpgrid(msm_ctx* ctx, const double* xyz, int N, const int* tris, int T, const double* maxsep, const double* orig_xyz,
+                   const double* abs_weights) {
+    CK(cudaSetDevice(ctx->device));
+    if (N <= 0) FAIL("msm_set_cpgrid: empty control grid");
+    ctx->N = N; ctx->Tcp = T;
+    ctx->k_begin = 0; ctx->k_end = N;
+    ctx->h_cp.assign(xyz, xyz + (size_t)N * 3);
+    if (upload(ctx, ctx->d_cp, xyz, (size_t)N * 3)) return 1;
+    if (upload(ctx, ctx->d_ocp, xyz, (size_t)N * 3)) return 1;
+    if (upload(ctx, ctx->d_orig, orig_xyz ? orig_xyz : xyz, (size_t)N * 3)) return 1;
+    if (maxsep) {
+        ctx->h_maxsep.assign(maxsep, maxsep + N);
+        if (upload(ctx, ctx->d_maxsep, maxsep, (size_t)N)) return 1;
+    } else ctx->h_maxsep.clear();
+    {
+        std::vector<double> aw(N, 1.0);
+        if (abs_weights) aw.assign(abs_weights, abs_weights + N);
+        if (upload_as_float(ctx, ctx->d_absw, aw.data(), (size_t)N)) return 1;
+    }
+    if (T > 0) {
+        for (int i = 0; i < 3 * T; i++)
+            if (tris[i] < 0 || tris[i] >= N) FAIL("msm_set_cpgrid: triangle index out of range");
+        if (upload(ctx, ctx->d_tris, tris, (size_t)T * 3)) return 1;
+        std::vector<int> off(N + 1, 0), idx((size_t)T * 3);
+        for (int i = 0; i < 3 * T; i++) off[tris[i] + 1]++;
+        for (int i = 0; i < N; i++) off[i + 1] += off[i];
+        std::vector<int> fill(off.begin(), off.end() - 1);
+        for (int t = 0; t < T; t++)
+            for (int j = 0; j < 3; j++) idx[fill[tris[3 * t + j]]++] = t;
+        if (upload(ctx, ctx->d_vt_off, off.data(), off.size())) return 1;
+        if (upload(ctx, ctx->d_vt_idx, idx.data(), idx.size())) return 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->rot_dirty = true;
+    ctx->have_patches = false;
+    ctx->have_unary = false;
+    return 0;
+}
+
+int msm_reset_cpgrid(msm_ctx* ctx, const double* xyz) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->N <= 0) FAIL("msm_set_cpgrid must be called first");
+    ctx->h_cp.assign(xyz, xyz + (size_t)ctx->N * 3);
+    if (upload(ctx, ctx->d_cp, xyz, (size_t)ctx->N * 3)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->rot_dirty = true;
+    ctx->have_patches = false;
+    ctx->have_unary = false;
+    return 0;
+}
+
+int msm_set_shard(msm_ctx* ctx, int k_begin, int k_end) {
+    if (k_begin < 0 || k_end > ctx->N || k_begin > k_end) FAIL("msm_set_shard: bad range");
+    ctx->k_begin = k_begin; ctx->k_end = k_end;
+    ctx->have_patches = false;
+    ctx->have_unary = false;
+    return 0;
+}
+
+int msm_set_labels(msm_ctx* ctx, const double* labels, int L, const double* centre) {
+    CK(cudaSetDevice(ctx->device));
+    if (L <= 0) FAIL("msm_set_labels: empty label set");
+    ctx->L = L;
+    for (int j = 0; j < 3; j++) ctx->centre[j] = centre[j];
+    if (upload(ctx, ctx->d_labels, labels, (size_t)L * 3)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->rot_dirty = true;
+    ctx->have_unary = false;
+    return 0;
+}
+
+int msm_set_pairs(msm_ctx* ctx, const int* pairs, int P) {
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < 2 * P; i++)
+        if (pairs[i] < 0 || pairs[i] >= ctx->N) FAIL("msm_set_pairs: node id out of range");
+    ctx->P = P;
+    if (upload(ctx, ctx->d_pairs, pairs, (size_t)P * 2)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_set_triplets(msm_ctx* ctx, const int* triplets, int T) {
+    CK(cudaSetDevice(ctx->device));
+    for (int i = 0; i < 3 * T; i++)
+        if (triplets[i] < 0 || triplets[i] >= ctx->N) FAIL("msm_set_triplets: node id out of range");
+    ctx->Tn = T;
+    if (upload(ctx, ctx->d_trip, triplets, (size_t)T * 3)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_set_group(msm_ctx* ctx, int S, int N_subj, int T_subj) {
+    if (S <= 0 || (long long)S * N_subj != ctx->N) FAIL("msm_set_group: S*N_subj must equal the control grid size");
+    ctx->S = S; ctx->N_subj = N_subj; ctx->T_subj = T_subj;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int msm_build_patches(msm_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->Vs <= 0 || ctx->N <= 0) FAIL("CostFunction::You must supply source and target meshes.");
+    if (ctx->h_maxsep.empty()) FAIL("msm_build_patches: set_spacings (maxsep) missing");
+    const int Ns = ctx->k_end - ctx->k_begin;
+    ctx->have_patches = false;
+    ctx->total = 0; ctx->maxP = 0;
+    if (Ns == 0) { ctx->have_patches = true; return 0; }
+    const int unc_cap = 1 << 20;
+    CK(ctx->d_counts.ensure((size_t)Ns * 4));
+    CK(ctx->d_off.ensure((size_t)(Ns + 1) * 4));
+    CK(ctx->d_unc.ensure((size_t)unc_cap * sizeof(int2)));
+    CK(ctx->d_unc_count.ensure(4));
+    CK(ctx->d_totmax.ensure(8));
+    CK(cudaMemsetAsync(ctx->d_unc_count.p, 0, 4, ctx->stream));
+    PatchArgs a;
+    a.k_begin = ctx->k_begin; a.k_end = ctx->k_end; a.V = ctx->Vs;
+    a.sxf = ctx->d_sxf.as<float>(); a.syf = ctx->d_syf.as<float>(); a.szf = ctx->d_szf.as<float>();
+    a.src = ctx->d_src.as<double>(); a.cp = ctx->d_cp.as<double>(); a.maxsep = ctx->d_maxsep.as<double>();
+    a.range = ctx->par.range;
+    a.counts = ctx->d_counts.as<int>();
+    a.unc = ctx->d_unc.as<int2>(); a.unc_cap = unc_cap; a.unc_count = ctx->d_unc_count.as<int>();
+    a.acc_off = nullptr; a.acc_idx = nullptr; a.off = nullptr; a.idx = nullptr;
+    Timer tm(ctx, "patches");
+    k_patch<false><<<Ns, 256, 0, ctx->stream>>>(a);
+    KLAUNCH_CHECK();
+    int n_unc = 0;
+    CK(cudaMemcpyAsync(&n_unc, ctx->d_unc_count.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_unc > unc_cap) FAIL("msm_build_patches: too many boundary ties");
+    bool have_acc = false;
+    if (n_unc > 0) {
+        // narrow phase on the host with the reference's own formula (src/DiscreteCostFunction.cpp:104-109)
+        std::vector<int2> unc(n_unc);
+        CK(cudaMemcpy(unc.data(), ctx->d_unc.p, (size_t)n_unc * sizeof(int2), cudaMemcpyDeviceToHost));
+        std::vector<std::vector<int>> acc(Ns);
+        const double RAD = 100.0;
+        for (const int2& u : unc) {
+            const double* c = &ctx->h_cp[3 * (size_t)u.x];
+            const double* s = &ctx->h_src[3 * (size_t)u.y];
+            const double X = c[0] - s[0], Y = c[1] - s[1], Z = c[2] - s[2];
+            const double norm = std::sqrt(X * X + Y * Y + Z * Z);
+            if ((2 * RAD * std::asin(norm / (2 * RAD))) < ctx->par.range * ctx->h_maxsep[u.x]) acc[u.x - ctx->k_begin].push_back(u.y);
+        }
+        std::vector<int> aoff(Ns + 1, 0), aidx;
+        for (int r = 0; r < Ns; r++) {
+            std::sort(acc[r].begin(), acc[r].end());
+            aoff[r + 1] = aoff[r] + (int)acc[r].size();
+            aidx.insert(aidx.end(), acc[r].begin(), acc[r].end());
+        }
+        if (upload(ctx, ctx->d_acc_off, aoff.data(), aoff.size())) return 1;
+        if (upload(ctx, ctx->d_acc_idx, aidx.data(), aidx.size())) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
+        have_acc = true;
+    }
+    k_patch_scan<<<1, 1024, 0, ctx->stream>>>(Ns, ctx->d_counts.as<int>(), have_acc ? ctx->d_acc_off.as<int>() : nullptr, ctx->d_off.as<int>(),
+                                              ctx->d_totmax.as<int>());
+    KLAUNCH_CHECK();
+    int totmax[2];
+    CK(cudaMemcpyAsync(totmax, ctx->d_totmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->total = totmax[0]; ctx->maxP = totmax[1];
+    const size_t tot = std::max<long long>(ctx->total, 1);
+    CK(ctx->d_idx.ensure(tot * 4));
+    a.acc_off = have_acc ? ctx->d_acc_off.as<int>() : nullptr;
+    a.acc_idx = have_acc ? ctx->d_acc_idx.as<int>() : nullptr;
+    a.off = ctx->d_off.as<int>(); a.idx = ctx->d_idx.as<int>();
+    k_patch<true><<<Ns, 256, 0, ctx->stream>>>(a);
+    KLAUNCH_CHECK();
+    // packed sample streams
+    const int Cp = ctx->multivariate ? 4 * ((ctx->Cs + 3) / 4) : 1;
+    if (!ctx->multivariate && ctx->Cs != 1) FAIL("univariate cost function needs C == 1 (src/DiscreteModel.cpp:22-36)");
+    ctx->pack_cp = Cp;
+    CK(ctx->d_px.ensure(tot * 4)); CK(ctx->d_py.ensure(tot * 4)); CK(ctx->d_pz.ensure(tot * 4));
+    CK(ctx->d_pa.ensure(tot * 4 * Cp)); CK(ctx->d_pw.ensure(tot * 4 * Cp));
+    if (ctx->total > 0) {
+        k_patch_pack<<<(unsigned)((ctx->total + 255) / 256), 256, 0, ctx->stream>>>(
+            (int)ctx->total, Cp, ctx->Cs, ctx->wrows, ctx->Vs, ctx->d_idx.as<int>(), ctx->d_sxf.as<float>(), ctx->d_syf.as<float>(),
+            ctx->d_szf.as<float>(), ctx->d_sfeat.as<float>(), ctx->d_swgt.as<float>(), ctx->d_px.as<float>(), ctx->d_py.as<float>(),
+            ctx->d_pz.as<float>(), ctx->d_pa.as<float>(), ctx->d_pw.as<float>());
+        KLAUNCH_CHECK();
+    }
+    ctx->have_patches = true;
+    ctx->have_unary = false;
+    return 0;
+}
+
+int msm_patch_count(msm_ctx* ctx, long long* total) {
+    if (!ctx->have_patches) FAIL("msm_build_patches must be called first");
+    *total = ctx->total;
+    return 0;
+}
+
+int msm_get_patches(msm_ctx* ctx, int* offsets, int* idx) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_patches) FAIL("msm_build_patches must be called first");
+    const int Ns = ctx->k_end - ctx->k_begin;
+    std::vector<int> off(Ns + 1, 0);
+    if (Ns > 0) CK(cudaMemcpyAsync(off.data(), ctx->d_off.p, (size_t)(Ns + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->total > 0) CK(cudaMemcpyAsync(idx, ctx->d_idx.p, (size_t)ctx->total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k <= ctx->N; k++) {
+        if (k <= ctx->k_begin) offsets[k] = 0;
+        else if (k <= ctx->k_end) offsets[k] = off[k - ctx->k_begin];
+        else offsets[k] = (int)ctx->total;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_target) FAIL("CostFunction::You must supply source and target meshes.");
+    if (!ctx->have_patches) FAIL("get_source_data (msm_build_patches) must run before computeUnaryCosts");
+    if (ctx->Ct != ctx->Cs) FAIL("source and target feature dimensions differ");
+    if (ensure_label_rot(ctx)) return 1;
+    if (ensure_face_feat(ctx)) return 1;
+    const int Ns = ctx->k_end - ctx->k_begin;
+    if (Ns == 0) return 0;
+    const int CQ = ctx->face_feat_cq;
+    const int Cp = CQ == 0 ? 1 : 4 * CQ;
+    const int L = ctx->L, Pmax = std::max(ctx->maxP, 1);
+    // label groups: fit shared memory (<= ~56 KB so several CTAs share an SM) and expose >= 4 CTAs per SM
+    auto smem_for = [&](int Lg) { return (size_t)4 * ((size_t)(3 + 2 * Cp) * Pmax + (size_t)Lg * 12 + (size_t)Lg * Pmax); };
+    int Lg = L;
+    while (Lg > 1 && smem_for(Lg) > 56 * 1024) Lg--;
+    const int want_ctas = 4 * 148;
+    if ((long long)Ns * ((L + Lg - 1) / Lg) < want_ctas) {
+        int G = (want_ctas + Ns - 1) / Ns;
+        Lg = std::min(Lg, std::max(1, (L + G - 1) / G));
+    }
+    const size_t smem = smem_for(Lg);
+    if (smem > 200 * 1024) FAIL("msm_unary_table: control-point patch too large for one CTA's shared memory");
+    UnaryArgs a;
+    a.k_begin = ctx->k_begin; a.Ns = Ns; a.L = L; a.Lg = Lg; a.G = (L + Lg - 1) / Lg;
+    a.off = ctx->d_off.as<int>();
+    a.px = ctx->d_px.as<float>(); a.py = ctx->d_py.as<float>(); a.pz = ctx->d_pz.as<float>();
+    a.pa = ctx->d_pa.as<float>(); a.pw = ctx->d_pw.as<float>();
+    a.total = (int)ctx->total;
+    a.Kf = ctx->d_Kf.as<float>();
+    a.cp = ctx->d_cp.as<double>();
+    a.absw = ctx->d_absw.as<float>();
+    a.face_feat = ctx->d_face_feat.as<float>();
+    a.ico = ico_dev(ctx);
+    a.simmeasure = ctx->par.simmeasure;
+    a.out = d_out;
+    const unsigned grid = (unsigned)((long long)Ns * a.G);
+    Timer tm(ctx, "unary");
+#define LAUNCH_UNARY(Q)                                                                                             \
+    do {                                                                                                            \
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_unary<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_unary<Q><<<grid, 256, smem, ctx->stream>>>(a);                                                            \
+    } while (0)
+    switch (CQ) {
+        case 0: LAUNCH_UNARY(0); break;
+        case 1: LAUNCH_UNARY(1); break;
+        case 2: LAUNCH_UNARY(2); break;
+        case 3: LAUNCH_UNARY(3); break;
+        case 4: LAUNCH_UNARY(4); break;
+        default: FAIL("unsupported channel count");
+    }
+#undef LAUNCH_UNARY
+    KLAUNCH_CHECK();
+    return 0;
+}
+
+int msm_unary_table(msm_ctx* ctx, double* out) {
+    CK(cudaSetDevice(ctx->device));
+    const int Ns = ctx->k_end - ctx->k_begin, L = ctx->L, N = ctx->N;
+    CK(ctx->d_unary.ensure(std::max<size_t>((size_t)L * Ns, 1) * 4));
+    if (msm_unary_table_dev(ctx, ctx->d_unary.as<float>())) return 1;
+    if (Ns == 0) return 0;
+    CK(ctx->h_pin.ensure((size_t)L * Ns * 4));
+    CK(cudaMemcpyAsync(ctx->h_pin.p, ctx->d_unary.p, (size_t)L * Ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const float* h = ctx->h_pin.as<float>();
+    ctx->h_unary.resize((size_t)L * N);
+    for (int l = 0; l < L; l++)
+        for (int r = 0; r < Ns; r++) {
+            const double v = (double)h[(size_t)l * Ns + r];
+            out[(size_t)l * N + ctx->k_begin + r] = v;
+            ctx->h_unary[(size_t)l * N + ctx->k_begin + r] = v;
+        }
+    ctx->have_unary = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int msm_triplet_costs(msm_ctx* ctx, int n, const int* q, double* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (check_triplets(ctx)) return 1;
+    if (n <= 0) return 0;
+    for (int i = 0; i < n; i++) {
+        if (q[4 * i] < 0 || q[4 * i] >= ctx->Tn) FAIL("msm_triplet_costs: triplet index out of range");
+        for (int j = 1; j < 4; j++)
+            if (q[4 * i + j] < 0 || q[4 * i + j] >= ctx->L) FAIL("msm_triplet_costs: label out of range");
+    }
+    CK(ctx->d_scratch.ensure((size_t)n * 16));
+    CK(ctx->d_scratch2.ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(ctx->d_scratch.p, q, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timer tm(ctx, "triplet_queries");
+        k_triplet_queries<<<(n + 127) / 128, 128, 0, ctx->stream>>>(trip_args(ctx), n, ctx->d_scratch.as<int>(), ctx->d_scratch2.as<double>());
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_triplet_table_dev(msm_ctx* ctx, int t0, int t1, float* d_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (check_triplets(ctx)) return 1;
+    if (t0 < 0 || t1 > ctx->Tn || t0 > t1) FAIL("msm_triplet_table: bad triplet range");
+    if (t0 == t1) return 0;
+    const int L = ctx->L;
+    const size_t smem = (size_t)9 * L * sizeof(double) + (size_t)L * L * L * sizeof(float);
+    if (smem > 200 * 1024) FAIL("msm_triplet_table: label set too large for the full table kernel");
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_triplet_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Timer tm(ctx, "triplet_table");
+    k_triplet_table<<<t1 - t0, 256, smem, ctx->stream>>>(trip_args(ctx), t0, d_out);
+    KLAUNCH_CHECK();
+    return 0;
+}
+
+int msm_triplet_table(msm_ctx* ctx, int t0, int t1, float* out) {
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)std::max(0, t1 - t0) * ctx->L * ctx->L * ctx->L;
+    CK(ctx->d_scratch.ensure(std::max<size_t>(n, 1) * 4));
+    if (msm_triplet_table_dev(ctx, t0, t1, ctx->d_scratch.as<float>())) return 1;
+    if (n) CK(cudaMemcpyAsync(out, ctx->d_scratch.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float* d_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (check_triplets(ctx)) return 1;
+    if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
+    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * ctx->Tn * 8;
+    Timer tm(ctx, "triplet_moves");
+    k_triplet_moves<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, d_labeling, alpha, d_out);
+    KLAUNCH_CHECK();
+    return 0;
+}
+
+int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (check_triplets(ctx)) return 1;
+    if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
+    for (int i = 0; i < ctx->N; i++)
+        if (labeling[i] < 0 || labeling[i] >= ctx->L) FAIL("msm_triplet_moves: labeling out of range");
+    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * ctx->Tn * 8;
+    CK(ctx->d_scratch.ensure((size_t)ctx->N * 4));
+    CK(ctx->d_scratch2.ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timer tm(ctx, "triplet_moves");
+        k_triplet_moves<double><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha,
+                                                                                   ctx->d_scratch2.as<double>());
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int check_pairs(msm_ctx* ctx) {
+    if (ctx->P <= 0) FAIL("set_pairs must be called first");
+    if (ctx->Tcp <= 0) FAIL("pairwise regulariser needs the control grid faces (fold test)");
+    if (ctx->par.mvdmax <= 0) FAIL("pairwise regulariser needs MVDmax (set_spacings)");
+    return ensure_label_rot(ctx);
+}
+
+int msm_pair_table_dev(msm_ctx* ctx, float* d_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (check_pairs(ctx)) return 1;
+    const long long n = (long long)ctx->P * ctx->L * ctx->L;
+    Timer tm(ctx, "pair_table");
+    k_pair_table<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(pair_args(ctx), d_out);
+    KLAUNCH_CHECK();
+    return 0;
+}
+
+int msm_pair_table(msm_ctx* ctx, float* out) {
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->P * ctx->L * ctx->L;
+    CK(ctx->d_scratch.ensure(std::max<size_t>(n, 1) * 4));
+    if (msm_pair_table_dev(ctx, ctx->d_scratch.as<float>())) return 1;
+    CK(cudaMemcpyAsync(out, ctx->d_scratch.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int msm_locate(msm_ctx* ctx, const double* pts, int M, int* tri, double* w) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_target) FAIL("msm_set_target must be called first");
+    if (M <= 0) return 0;
+    CK(ctx->d_scratch.ensure((size_t)M * 24));
+    CK(ctx->d_scratch2.ensure((size_t)M * (24 + 4)));
+    double* d_w = ctx->d_scratch2.as<double>();
+    int* d_tri = reinterpret_cast<int*>(d_w + (size_t)3 * M);
+    CK(cudaMemcpyAsync(ctx->d_scratch.p, pts, (size_t)M * 24, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timer tm(ctx, "locate");
+        k_locate<<<(M + 255) / 256, 256, 0, ctx->stream>>>(ico_dev(ctx), M, ctx->d_scratch.as<double>(), ctx->d_leaf_user.as<int>(),
+                                                          ctx->d_leaf_perm.as<unsigned char>(), d_tri, d_w);
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(tri, d_tri, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (w) CK(cudaMemcpyAsync(w, d_w, (size_t)M * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]) {
+    CK(cudaSetDevice(ctx->device));
+    sums[0] = sums[1] = sums[2] = 0.0;
+    for (int i = 0; i < ctx->N; i++)
+        if (labeling[i] < 0 || labeling[i] >= ctx->L) FAIL("msm_total_cost: labeling out of range");
+    if (ctx->have_unary)
+        for (int k = ctx->k_begin; k < ctx->k_end; k++) sums[0] += ctx->h_unary[(size_t)labeling[k] * ctx->N + k];
+    if (ctx->P > 0 && !ctx->par.group) {
+        if (check_pairs(ctx)) return 1;
+        std::vector<int> q((size_t)ctx->P * 3);
+        std::vector<int> hp((size_t)ctx->P * 2);
+        CK(cudaMemcpy(hp.data(), ctx->d_pairs.p, hp.size() * 4, cudaMemcpyDeviceToHost));
+        for (int p = 0; p < ctx->P; p++) { q[3 * p] = p; q[3 * p + 1] = labeling[hp[2 * p]]; q[3 * p + 2] = labeling[hp[2 * p + 1]]; }
+        CK(ctx->d_scratch.ensure(q.size() * 4));
+        CK(ctx->d_scratch2.ensure((size_t)ctx->P * 8));
+        CK(cudaMemcpyAsync(ctx->d_scratch.p, q.data(), q.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_pair_queries<<<(ctx->P + 127) / 128, 128, 0, ctx->stream>>>(pair_args(ctx), ctx->P, ctx->d_scratch.as<int>(), ctx->d_scratch2.as<double>());
+        KLAUNCH_CHECK();
+        std::vector<double> r(ctx->P);
+        CK(cudaMemcpyAsync(r.data(), ctx->d_scratch2.p, (size_t)ctx->P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (double v : r) sums[1] += v;
+    }
+    if (ctx->Tn > 0) {
+        std::vector<int> ht((size_t)ctx->Tn * 3), q((size_t)ctx->Tn * 4);
+        CK(cudaMemcpy(ht.data(), ctx->d_trip.p, ht.size() * 4, cudaMemcpyDeviceToHost));
+        for (int t = 0; t < ctx->Tn; t++) {
+            q[4 * t] = t; q[4 * t + 1] = labeling[ht[3 * t]]; q[4 * t + 2] = labeling[ht[3 * t + 1]]; q[4 * t + 3] = labeling[ht[3 * t + 2]];
+        }
+        std::vector<double> r(ctx->Tn);
+        if (msm_triplet_costs(ctx, ctx->Tn, q.data(), r.data())) return 1;
+        for (double v : r) sums[2] += v;
+    }
+    return 0;
+}
+
+long long msm_launch_count(const msm_ctx* ctx) { return ctx->launches; }
+int msm_set_timing(msm_ctx* ctx, int enabled) { ctx->timing = enabled != 0; return 0; }
+double msm_last_kernel_ms(const msm_ctx* ctx, const char* family) {
+    auto it = ctx->last_ms.find(family);
+    return it == ctx->last_ms.end() ? -1.0 : (double)it->second;
+}
+
+}  // extern "C"

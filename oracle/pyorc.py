@@ -1,0 +1,274 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/liborc.so (the CPU restatement of the reference hot path, oracle/oracle.h).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+PARITY UNPINNED: the reference has no tests or golden vectors for this path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborc.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_capi.cpp", "oracle.h", "geom.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liborc.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_cf_create.restype = C.c_void_p
+        _LIB.orc_gc_create.restype = C.c_void_p
+        for f in ("orc_mesh_meanangle", "orc_corr", "orc_strain", "orc_cf_unary_cost", "orc_cf_pair_cost", "orc_cf_total", "orc_cf_meanangle"):
+            getattr(_LIB, f).restype = C.c_double
+    return _LIB
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_ip)
+
+
+def icosphere(level, radius=100.0):
+    nv, nf = C.c_int(), C.c_int()
+    lib().orc_icosphere_counts(level, C.byref(nv), C.byref(nf))
+    xyz = np.empty((nv.value, 3), np.float64)
+    tris = np.empty((nf.value, 3), np.int32)
+    lib().orc_icosphere(level, C.c_double(radius), xyz.ctypes.data_as(c_dp), tris.ctypes.data_as(c_ip))
+    return xyz, tris
+
+
+def rotation_matrix(a, b):
+    a, pa = _d(a); b, pb = _d(b)
+    out = np.empty((3, 3), np.float64)
+    lib().orc_rotation_matrix(pa, pb, out.ctypes.data_as(c_dp))
+    return out
+
+
+def label_grid(sgres, maxs_dist, cap=4096):
+    s = np.empty((cap, 3)); b = np.empty((cap, 3)); c = np.empty(3)
+    ns, nb = C.c_int(), C.c_int()
+    lib().orc_label_grid(sgres, C.c_double(maxs_dist), cap, s.ctypes.data_as(c_dp), C.byref(ns), b.ctypes.data_as(c_dp),
+                         C.byref(nb), c.ctypes.data_as(c_dp))
+    assert ns.value <= cap and nb.value <= cap
+    return s[:ns.value].copy(), b[:nb.value].copy(), c
+
+
+def spacings(xyz, tris):
+    xyz, px = _d(xyz); tris, pt = _i(tris)
+    ms = np.empty(len(xyz)); mx, mvd = C.c_double(), C.c_double()
+    lib().orc_spacings(px, len(xyz), pt, len(tris), ms.ctypes.data_as(c_dp), C.byref(mx), C.byref(mvd))
+    return ms, mx.value, mvd.value
+
+
+def triplets(xyz, tris):
+    xyz, px = _d(xyz); tris, pt = _i(tris)
+    out = np.empty((len(tris), 3), np.int32)
+    lib().orc_triplets(px, len(xyz), pt, len(tris), out.ctypes.data_as(c_ip))
+    return out
+
+
+def pairs(xyz, tris):
+    xyz, px = _d(xyz); tris, pt = _i(tris)
+    cap = 3 * len(xyz)
+    out = np.empty((cap, 2), np.int32)
+    n = lib().orc_pairs(px, len(xyz), pt, len(tris), out.ctypes.data_as(c_ip), cap)
+    return out[:n].copy()
+
+
+def mesh_meanangle(xyz, tris):
+    xyz, px = _d(xyz); tris, pt = _i(tris)
+    return lib().orc_mesh_meanangle(px, len(xyz), pt, len(tris))
+
+
+def rotations(centre, cps):
+    centre, pc = _d(centre); cps, pp = _d(cps)
+    out = np.empty((len(cps), 3, 3))
+    lib().orc_rotations(pc, pp, len(cps), out.ctypes.data_as(c_dp))
+    return out
+
+
+def corr(a, b, w=None):
+    a, pa = _d(a); b, pb = _d(b)
+    if w is None:
+        return lib().orc_corr(pa, pb, None, len(a), 0)
+    w, pw = _d(w)
+    return lib().orc_corr(pa, pb, pw, len(a), 1)
+
+
+def strain(t0, t1, mu=0.4, kappa=1.6, k_exp=2.0, which=0):
+    t0, p0 = _d(t0); t1, p1 = _d(t1)
+    return lib().orc_strain(p0, p1, C.c_double(mu), C.c_double(kappa), C.c_double(k_exp), which)
+
+
+def locate(xyz, tris, pts, brute=False, orthogonal=False):
+    xyz, px = _d(xyz); tris, pt = _i(tris); pts, pp = _d(pts)
+    tri = np.empty(len(pts), np.int32); w = np.empty((len(pts), 3))
+    lib().orc_locate(px, len(xyz), pt, len(tris), pp, len(pts), tri.ctypes.data_as(c_ip), w.ctypes.data_as(c_dp), int(brute),
+                     int(orthogonal))
+    return tri, w
+
+
+class CostFunction:
+    """Mirror of NonLinearSRegDiscreteCostFunction (+Uni/Multi variants), src/DiscreteCostFunction.{h,cpp}."""
+
+    def __init__(self):
+        self.h = C.c_void_p(lib().orc_cf_create())
+        self.N = self.L = self.T = self.P = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_cf_destroy(self.h); self.h = None
+
+    def set_params(self, lam=1.0, rexp=2.0, mu=0.4, kappa=1.6, k_exp=2.0, rng=1.0, simmeasure=2, rmode=3, dweight=False,
+                   anorm=False, threads=1, bary_orth=False):
+        lib().orc_cf_set_params(self.h, C.c_double(lam), C.c_double(rexp), C.c_double(mu), C.c_double(kappa), C.c_double(k_exp),
+                                C.c_double(rng), simmeasure, rmode, int(dweight), int(anorm), threads, int(bary_orth))
+
+    def set_meshes(self, txyz, ttris, sxyz, cxyz, ctris):
+        txyz, p1 = _d(txyz); ttris, p2 = _i(ttris); sxyz, p3 = _d(sxyz); cxyz, p4 = _d(cxyz); ctris, p5 = _i(ctris)
+        self.N, self.T, self.Vs, self.Vt = len(cxyz), len(ctris), len(sxyz), len(txyz)
+        lib().orc_cf_set_meshes(self.h, p1, len(txyz), p2, len(ttris), p3, len(sxyz), p4, len(cxyz), p5, len(ctris))
+
+    def set_orig(self, xyz):
+        xyz, p = _d(xyz); lib().orc_cf_set_orig(self.h, p, len(xyz))
+
+    def set_features(self, ref, inp, multivariate=None):
+        ref = np.atleast_2d(ref); inp = np.atleast_2d(inp)
+        ref, pr = _d(ref); inp, pi = _d(inp)
+        if multivariate is None:
+            multivariate = ref.shape[0] > 1
+        self.C = ref.shape[0]
+        lib().orc_cf_set_features(self.h, ref.shape[0], pr, ref.shape[1], pi, inp.shape[1], int(multivariate))
+
+    def set_cfweight(self, w):
+        w = np.atleast_2d(w); w, p = _d(w)
+        lib().orc_cf_set_cfweight(self.h, w.shape[0], p, w.shape[1])
+
+    def set_absweights(self, aw):
+        aw, p = _d(aw); lib().orc_cf_set_absweights(self.h, p, len(aw))
+
+    def set_spacings(self, maxsep, mvdmax):
+        maxsep, p = _d(maxsep); lib().orc_cf_set_spacings(self.h, p, len(maxsep), C.c_double(mvdmax))
+
+    def set_labels(self, labels, rot):
+        labels, pl = _d(labels); rot, pr = _d(rot)
+        self.L = len(labels)
+        lib().orc_cf_set_labels(self.h, pl, len(labels), pr, len(rot))
+
+    def reset_source(self, xyz):
+        xyz, p = _d(xyz); lib().orc_cf_reset_source(self.h, p)
+
+    def reset_cpgrid(self, xyz):
+        xyz, p = _d(xyz); lib().orc_cf_reset_cpgrid(self.h, p)
+
+    def set_pairs(self, pairs_):
+        pairs_, p = _i(pairs_); self.P = len(pairs_); lib().orc_cf_set_pairs(self.h, p, len(pairs_))
+
+    def set_triplets(self, t):
+        t, p = _i(t); self.T = len(t); lib().orc_cf_set_triplets(self.h, p, len(t))
+
+    def get_source_data(self, k0=None, k1=None):
+        if k0 is None:
+            lib().orc_cf_get_source_data(self.h)
+        else:
+            lib().orc_cf_get_source_data_range(self.h, k0, k1)
+
+    def patches(self):
+        sizes = np.empty(self.N, np.int32)
+        lib().orc_cf_patch_sizes(self.h, sizes.ctypes.data_as(c_ip))
+        out = []
+        for k in range(self.N):
+            a = np.empty(sizes[k], np.int32)
+            lib().orc_cf_patch(self.h, k, a.ctypes.data_as(c_ip))
+            out.append(a)
+        return out
+
+    def unary_costs(self, k0=None, k1=None):
+        if k0 is None:
+            out = np.empty((self.L, self.N))
+            lib().orc_cf_unary_costs(self.h, out.ctypes.data_as(c_dp))
+        else:
+            out = np.empty((self.L, k1 - k0))
+            lib().orc_cf_unary_costs_range(self.h, k0, k1, out.ctypes.data_as(c_dp))
+        return out
+
+    def unary_cost(self, node, label):
+        return lib().orc_cf_unary_cost(self.h, node, label)
+
+    def triplet_costs(self, q):
+        q, p = _i(q)
+        out = np.empty(len(q))
+        lib().orc_cf_triplet_costs(self.h, len(q), p, out.ctypes.data_as(c_dp))
+        return out
+
+    def triplet_table(self, t0=0, t1=None):
+        t1 = self.T if t1 is None else t1
+        out = np.empty((t1 - t0, self.L, self.L, self.L))
+        lib().orc_cf_triplet_table(self.h, t0, t1, out.ctypes.data_as(c_dp))
+        return out
+
+    def pair_table(self):
+        out = np.empty((self.P, self.L, self.L))
+        lib().orc_cf_pair_table(self.h, out.ctypes.data_as(c_dp))
+        return out
+
+    def pair_cost(self, p, la, lb):
+        return lib().orc_cf_pair_cost(self.h, p, la, lb)
+
+    def total(self, labeling, use_unary=True):
+        labeling, p = _i(labeling)
+        return lib().orc_cf_total(self.h, p, int(use_unary))
+
+    def meanangle(self):
+        return lib().orc_cf_meanangle(self.h)
+
+
+class GroupCost:
+    """Mirror of DiscreteGroupCostFunction, src/DiscreteGroupCostFunction.{h,cpp}."""
+
+    def __init__(self):
+        self.h = C.c_void_p(lib().orc_gc_create())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_gc_destroy(self.h); self.h = None
+
+    def set(self, lam, rexp, mu, kappa, cp_xyz, cp_tris, orig_xyz, labels, rot, triplets_):
+        cp_xyz, p1 = _d(cp_xyz); cp_tris, p2 = _i(cp_tris); orig_xyz, p3 = _d(orig_xyz)
+        labels, p4 = _d(labels); rot, p5 = _d(rot); triplets_, p6 = _i(triplets_)
+        S, N = cp_xyz.shape[0], cp_xyz.shape[1]
+        self.L = len(labels)
+        lib().orc_gc_set(self.h, C.c_double(lam), C.c_double(rexp), C.c_double(mu), C.c_double(kappa), S, p1, N, p2, len(cp_tris),
+                         p3, p4, len(labels), p5, p6)
+
+    def triplet_costs(self, q):
+        q, p = _i(q); out = np.empty(len(q))
+        lib().orc_gc_triplet_costs(self.h, len(q), p, out.ctypes.data_as(c_dp))
+        return out
+
+    def set_patches(self, off, keys, vals, pairs_):
+        off = np.ascontiguousarray(off, np.int64); keys, pk = _i(keys); vals, pv = _d(vals); pairs_, pp = _i(pairs_)
+        lib().orc_gc_set_patches(self.h, len(off) - 1, off.ctypes.data_as(C.POINTER(C.c_longlong)), pk, pv, pp, len(pairs_))
+
+    def pair_costs(self, q):
+        q, p = _i(q); out = np.empty(len(q))
+        lib().orc_gc_pair_costs(self.h, len(q), p, self.L, out.ctypes.data_as(c_dp))
+        return out
