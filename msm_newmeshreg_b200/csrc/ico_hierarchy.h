@@ -38,6 +38,10 @@ struct IcoHierarchy {
     double centre[20][3];
     // per hierarchy node (heap order: node 0 = root, children of n are 4n+1..4n+4): (n_ab, n_bc, n_ca)
     std::vector<std::array<double, 3>> ntab;
+    // corner vertex ids of every face of every level (level l: index base*4^l + path) and the unit vertex directions:
+    // kept for the per-level hint tables (build_hint_level)
+    std::vector<std::vector<std::array<int, 3>>> lvl_vid;
+    std::vector<std::array<double, 3>> unit;
     std::string error;
 
     static void norm3(double* v) {
@@ -137,6 +141,8 @@ struct IcoHierarchy {
         std::vector<char> ntab_set(nnodes, 0);
 
         struct Item { int a, b, c; long node; long path; int level; };
+        lvl_vid.assign(depth + 1, {});
+        for (int l = 0; l <= depth; l++) lvl_vid[l].assign((size_t)20 << (2 * l), {0, 0, 0});
         bool ok = true;
         for (int b = 0; b < 20 && ok; b++) {
             // dual basis and centre
@@ -155,6 +161,7 @@ struct IcoHierarchy {
             while (!stack.empty() && ok) {
                 Item it = stack.back();
                 stack.pop_back();
+                lvl_vid[it.level][((size_t)b << (2 * it.level)) + it.path] = {it.a, it.b, it.c};
                 if (it.level == depth) {
                     long leaf = (long)b * nleaf_per_base + it.path;
                     auto fm = facemap.find(tkey(it.a, it.b, it.c));
@@ -189,9 +196,54 @@ struct IcoHierarchy {
             }
         }
         if (!ok) return false;
+        unit = u;
         for (int t = 0; t < nf; t++)
             if (user_to_leaf[t] < 0) { error = "target mesh has faces outside the icosphere hierarchy"; return false; }
         return true;
+    }
+
+    // Hint tables for level h: per face the dual basis of its (unit) corner directions, and per edge the neighbouring
+    // face with the 3x3 change of corner coordinates (x_nbr = T * x_face).  Edge e is the one opposite corner e.
+    void build_hint_level(int h, std::vector<double>& hdual, std::vector<int>& hnbr, std::vector<double>& hT) const {
+        const auto& fv = lvl_vid[h];
+        const size_t nfh = fv.size();
+        hdual.assign(nfh * 9, 0.0);
+        hnbr.assign(nfh * 3, -1);
+        hT.assign(nfh * 27, 0.0);
+        auto dual_of = [&](const std::array<int, 3>& f, double* d) {
+            const double* A = unit[f[0]].data(); const double* B = unit[f[1]].data(); const double* Cc = unit[f[2]].data();
+            double bxc[3] = {B[1] * Cc[2] - B[2] * Cc[1], B[2] * Cc[0] - B[0] * Cc[2], B[0] * Cc[1] - B[1] * Cc[0]};
+            double cxa[3] = {Cc[1] * A[2] - Cc[2] * A[1], Cc[2] * A[0] - Cc[0] * A[2], Cc[0] * A[1] - Cc[1] * A[0]};
+            double axb[3] = {A[1] * B[2] - A[2] * B[1], A[2] * B[0] - A[0] * B[2], A[0] * B[1] - A[1] * B[0]};
+            double D = A[0] * bxc[0] + A[1] * bxc[1] + A[2] * bxc[2];
+            for (int j = 0; j < 3; j++) { d[j] = bxc[j] / D; d[3 + j] = cxa[j] / D; d[6 + j] = axb[j] / D; }
+        };
+        for (size_t f = 0; f < nfh; f++) dual_of(fv[f], &hdual[9 * f]);
+        std::unordered_map<int64_t, std::pair<int, int>> edge_face;  // sorted edge -> first (face, edge slot)
+        edge_face.reserve(nfh * 3);
+        auto ekey = [&](int a, int b) { return (int64_t)std::min(a, b) * V + std::max(a, b); };
+        for (size_t f = 0; f < nfh; f++)
+            for (int e = 0; e < 3; e++) {
+                int64_t k = ekey(fv[f][(e + 1) % 3], fv[f][(e + 2) % 3]);
+                auto it = edge_face.find(k);
+                if (it == edge_face.end()) edge_face[k] = {(int)f, e};
+                else {
+                    int g = it->second.first, ge = it->second.second;
+                    hnbr[3 * f + e] = g;
+                    hnbr[3 * g + ge] = (int)f;
+                }
+            }
+        for (size_t f = 0; f < nfh; f++)
+            for (int e = 0; e < 3; e++) {
+                int g = hnbr[3 * f + e];
+                if (g < 0) continue;
+                // T = Dual_g (rows) * M_f (columns = unit corners of f)
+                for (int r = 0; r < 3; r++)
+                    for (int c = 0; c < 3; c++) {
+                        const double* col = unit[fv[f][c]].data();
+                        hT[27 * f + 9 * e + 3 * r + c] = hdual[9 * g + 3 * r] * col[0] + hdual[9 * g + 3 * r + 1] * col[1] + hdual[9 * g + 3 * r + 2] * col[2];
+                    }
+            }
     }
 };
 

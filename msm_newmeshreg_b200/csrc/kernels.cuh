@@ -186,184 +186,56 @@ __global__ void __launch_bounds__(1024) k_patch_scan(int n, const int* __restric
     if (tid == 0) { off[n] = s_carry; total_max[0] = s_carry; total_max[1] = s_max; }
 }
 
-// gather the packed per-patch sample streams (SoA over the global sample index) — coalesced reads in k_unary
-__global__ void __launch_bounds__(256) k_patch_pack(int total, int Cp, int C, int wrows, int V, const int* __restrict__ idx,
-                                                    const float* __restrict__ sxf, const float* __restrict__ syf,
-                                                    const float* __restrict__ szf, const float* __restrict__ feat /*[C][V]*/,
+// gather the packed per-patch sample streams (SoA over the global sample index) — coalesced reads in k_unary.
+// Coordinates are stored as offsets from the patch's control point, r = SRC_i - CP_k, formed in fp64: small numbers
+// keep full relative precision in fp32 (absolute coordinates at |x|~100 would not resolve an ico7 triangle to 1e-5).
+// Univariate: source values are stored relative to the patch's first sample (Pearson is shift invariant), so the
+// fp32 copy resolves the variation inside the patch rather than the field's absolute level.
+__global__ void __launch_bounds__(128) k_patch_pack(int k_begin, int total, int Cp, int C, int wrows, int V, int univariate,
+                                                    const int* __restrict__ off, const int* __restrict__ idx, const double* __restrict__ src,
+                                                    const double* __restrict__ cp, const double* __restrict__ feat /*[C][V]*/,
                                                     const float* __restrict__ wgt /*[wrows][V]*/, float* __restrict__ px,
                                                     float* __restrict__ py, float* __restrict__ pz, float* __restrict__ pa /*[Cp][total]*/,
                                                     float* __restrict__ pw) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= total) return;
-    int i = idx[s];
-    px[s] = sxf[i]; py[s] = syf[i]; pz[s] = szf[i];
-    for (int c = 0; c < Cp; c++) {
-        float a = 0.f, w = 0.f;  // padded channels carry zero weight: they drop out of every weighted sum
-        if (c < C) {
-            a = feat[(size_t)c * V + i];
-            w = (c < wrows) ? wgt[(size_t)c * V + i] : 1.0f;  // src/DiscreteCostFunction.cpp:404-407,474-477
+    const int row = blockIdx.x, k = k_begin + row;
+    const double ox = cp[3 * k], oy = cp[3 * k + 1], oz = cp[3 * k + 2];
+    const int s_begin = off[row], s_end = off[row + 1];
+    const double aref = (univariate && s_end > s_begin) ? feat[idx[s_begin]] : 0.0;
+    for (int s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
+        const int i = idx[s];
+        px[s] = (float)(src[3 * i] - ox); py[s] = (float)(src[3 * i + 1] - oy); pz[s] = (float)(src[3 * i + 2] - oz);
+        for (int c = 0; c < Cp; c++) {
+            float a = 0.f, w = 0.f;  // padded channels carry zero weight: they drop out of every weighted sum
+            if (c < C) {
+                a = (float)(feat[(size_t)c * V + i] - aref);
+                w = (c < wrows) ? wgt[(size_t)c * V + i] : 1.0f;  // src/DiscreteCostFunction.cpp:404-407,474-477
+            }
+            pa[(size_t)c * total + s] = a;
+            pw[(size_t)c * total + s] = w;
         }
-        pa[(size_t)c * total + s] = a;
-        pw[(size_t)c * total + s] = w;
     }
 }
 
-// face-packed target features: leaf -> (f[a][0..Cp), f[b][..], f[c][..]); univariate: float4 (fa, fb, fc, 0)
+// face-packed target features: leaf -> (f[a][0..Cp), f[b][..], f[c][..]).
+// Univariate: ONE float4 per face, (f_a hi, f_a lo, f_b - f_a, f_c - f_a) formed in fp64: the interpolated value
+// f_a + w_b (f_b-f_a) + w_c (f_c-f_a) then keeps ~1e-15 relative accuracy of the input although stored as 4 floats.
 __global__ void __launch_bounds__(256) k_face_pack(int F, int C, int Cp, int V, int univariate, const int* __restrict__ leaf_vid /*[F][3]*/,
-                                                   const float* __restrict__ feat /*[C][V]*/, float* __restrict__ out) {
+                                                   const double* __restrict__ feat /*[C][V]*/, float* __restrict__ out) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     int v0 = leaf_vid[3 * f], v1 = leaf_vid[3 * f + 1], v2 = leaf_vid[3 * f + 2];
     if (univariate) {
-        float4 o = make_float4(feat[v0], feat[v1], feat[v2], 0.f);
+        const double f0 = feat[v0], f1 = feat[v1], f2 = feat[v2];
+        const float hi = (float)f0;
+        float4 o = make_float4(hi, (float)(f0 - (double)hi), (float)(f1 - f0), (float)(f2 - f0));
         reinterpret_cast<float4*>(out)[f] = o;
     } else {
         float* o = out + (size_t)f * 3 * Cp;
         for (int c = 0; c < Cp; c++) {
-            o[c] = c < C ? feat[(size_t)c * V + v0] : 0.f;
-            o[Cp + c] = c < C ? feat[(size_t)c * V + v1] : 0.f;
-            o[2 * Cp + c] = c < C ? feat[(size_t)c * V + v2] : 0.f;
+            o[c] = c < C ? (float)feat[(size_t)c * V + v0] : 0.f;
+            o[Cp + c] = c < C ? (float)feat[(size_t)c * V + v1] : 0.f;
+            o[2 * Cp + c] = c < C ? (float)feat[(size_t)c * V + v2] : 0.f;
         }
-    }
-}
-
-// =========================================================================================================
-// k_unary — the unary data term (src/DiscreteCostFunction.cpp:306-313,412-448,483-526; similarities.cc:122-173).
-// One CTA per (control point, label group).  Phase 1: stage the CP's patch (coalesced SoA streams) and the label
-// rotations in shared memory.  Phase 2: every thread takes (label, sample) items: rotate, locate on the target
-// icosphere by scalar four-way descent, gather ONE face-packed feature vector, interpolate.  Phase 3: one warp per
-// label reduces the weighted Pearson correlation (two-pass, fp64 accumulators, fixed order -> deterministic).
-// CQ = number of float4 channel quads (0 = univariate).
-// =========================================================================================================
-struct UnaryArgs {
-    int k_begin, Ns, L, G, Lg;          // shard rows, labels, label groups, labels per group
-    const int* off;                     // [Ns+1]
-    const float* px; const float* py; const float* pz; const float* pa; const float* pw;  // packed streams
-    int total;                          // stride of pa/pw channels
-    const float* Kf;                    // [N][L][9]
-    const double* cp;                   // [N][3] (hint base face)
-    const float* absw;                  // [N]
-    const float* face_feat;             // face-packed target features
-    IcoDev ico;
-    int simmeasure;
-    float* out;                         // [L][Ns]
-};
-
-template <int CQ>
-__global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
-    constexpr int CP_ = CQ == 0 ? 1 : 4 * CQ;  // padded channel count
-    extern __shared__ float smem[];
-    const int row = blockIdx.x / a.G, g = blockIdx.x - row * a.G;
-    const int k = a.k_begin + row;
-    const int l0 = g * a.Lg, l1 = min(a.L, l0 + a.Lg), nl = l1 - l0;
-    const int s0 = a.off[row], P = a.off[row + 1] - s0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // smem carve: xyz[3][P] | a[CP_][P] | w[CP_][P] | K[Lg][12] | tbuf[Lg][P]
-    float* sx = smem; float* sy = sx + P; float* sz = sy + P;
-    float* sa = sz + P; float* sw = sa + CP_ * P;
-    float* sK = sw + CP_ * P;
-    float* tb = sK + a.Lg * 12;
-    __shared__ int s_hint;
-
-    for (int i = tid; i < P; i += 256) {
-        sx[i] = a.px[s0 + i]; sy[i] = a.py[s0 + i]; sz[i] = a.pz[s0 + i];
-#pragma unroll
-        for (int c = 0; c < CP_; c++) {
-            sa[c * P + i] = a.pa[(size_t)c * a.total + s0 + i];
-            sw[c * P + i] = a.pw[(size_t)c * a.total + s0 + i];
-        }
-    }
-    for (int i = tid; i < nl * 9; i += 256) {
-        int l = i / 9, e = i - l * 9;
-        sK[l * 12 + e] = a.Kf[((size_t)k * a.L + l0 + l) * 9 + e];
-    }
-    if (tid == 0) s_hint = ico_base_face<float>((float)a.cp[3 * k], (float)a.cp[3 * k + 1], (float)a.cp[3 * k + 2]);
-    __syncthreads();
-    const int hint = s_hint;
-    const int items = nl * P;
-    const float invP = 1.0f / (float)max(P, 1);
-
-    for (int j = tid; j < items; j += 256) {
-        const int l = (int)(((float)j + 0.5f) * invP);
-        const int i = j - l * P;
-        const float x = sx[i], y = sy[i], z = sz[i];
-        const float* K = sK + l * 12;
-        // p' = p + (R - I) p : the small correction is computed at full relative precision
-        const float qx = x + (K[0] * x + K[1] * y + K[2] * z);
-        const float qy = y + (K[3] * x + K[4] * y + K[5] * z);
-        const float qz = z + (K[6] * x + K[7] * y + K[8] * z);
-        float al, be, ga;
-        const int leaf = ico_locate<float>(a.ico, hint, qx, qy, qz, al, be, ga);
-        const float inv = 1.0f / (al + be + ga);
-        if (CQ == 0) {
-            const float4 f = __ldg(reinterpret_cast<const float4*>(a.face_feat) + leaf);
-            tb[j] = (al * f.x + be * f.y + ga * f.z) * inv;
-        } else {
-            // multivariate: Pearson across the channels of this one sample (src/DiscreteCostFunction.cpp:515-518)
-            const float4* ff = reinterpret_cast<const float4*>(a.face_feat) + (size_t)leaf * 3 * CQ;
-            float t[CP_];
-            const float wa = al * inv, wb = be * inv, wc = ga * inv;
-#pragma unroll
-            for (int q = 0; q < CQ; q++) {
-                const float4 f0 = __ldg(ff + q), f1 = __ldg(ff + CQ + q), f2 = __ldg(ff + 2 * CQ + q);
-                t[4 * q + 0] = wa * f0.x + wb * f1.x + wc * f2.x;
-                t[4 * q + 1] = wa * f0.y + wb * f1.y + wc * f2.y;
-                t[4 * q + 2] = wa * f0.z + wb * f1.z + wc * f2.z;
-                t[4 * q + 3] = wa * f0.w + wb * f1.w + wc * f2.w;
-            }
-            float W = 0.f, Sa = 0.f, St = 0.f;
-#pragma unroll
-            for (int c = 0; c < CP_; c++) {
-                const float w = sw[c * P + i];
-                W += w; Sa += w * sa[c * P + i]; St += w * t[c];
-            }
-            if (W > 0.f) { Sa /= W; St /= W; }
-            float pr = 0.f, va = 0.f, vt = 0.f;
-#pragma unroll
-            for (int c = 0; c < CP_; c++) {
-                const float w = sw[c * P + i];
-                const float da = sa[c * P + i] - Sa, dt = t[c] - St;
-                pr += w * da * dt; va += w * da * da; vt += w * dt * dt;
-            }
-            if (W > 0.f) { pr /= W; va /= W; vt /= W; }
-            const float rho = (va == 0.f || vt == 0.f) ? 0.f : pr / (sqrtf(va) * sqrtf(vt));
-            tb[j] = 1.0f - (1.0f + rho) * 0.5f;
-        }
-    }
-    __syncthreads();
-
-    const float AW = a.absw[k];
-    const bool pos = (a.simmeasure == 1 || a.simmeasure == 2);
-    for (int l = warp; l < nl; l += 8) {
-        const float* t = tb + l * P;
-        double cost;
-        if (CQ == 0) {
-            double W = 0, Sa = 0, St = 0;
-            for (int i = lane; i < P; i += 32) {
-                const double w = sw[i];
-                W += w; Sa += w * (double)sa[i]; St += w * (double)t[i];
-            }
-            W = warp_sum(W); Sa = warp_sum(Sa); St = warp_sum(St);
-            if (W > 0) { Sa /= W; St /= W; }
-            double pr = 0, va = 0, vt = 0;
-            for (int i = lane; i < P; i += 32) {
-                const double w = sw[i];
-                const double da = (double)sa[i] - Sa, dt = (double)t[i] - St;
-                pr += w * da * dt; va += w * da * da; vt += w * dt * dt;
-            }
-            pr = warp_sum(pr); va = warp_sum(va); vt = warp_sum(vt);
-            if (W > 0) { pr /= W; va /= W; vt /= W; }
-            const double rho = (va == 0.0 || vt == 0.0) ? 0.0 : pr / (sqrt(va) * sqrt(vt));
-            cost = (double)AW * (1.0 - (1.0 + rho) * 0.5);
-        } else {
-            double s = 0;
-            for (int i = lane; i < P; i += 32) s += (double)t[i];
-            s = warp_sum(s);
-            if (P > 0) s /= (double)P;
-            cost = (double)AW * s;
-        }
-        if (!pos) cost = -cost;
-        if (lane == 0) a.out[(size_t)(l0 + l) * a.Ns + row] = (float)cost;
     }
 }
 
@@ -630,3 +502,5 @@ __global__ void __launch_bounds__(256) k_locate(IcoDev ico, int M, const double*
 }
 
 }  // namespace msm
+
+#include "unary.cuh"

@@ -12,6 +12,21 @@ struct IcoDev {
     int leaf_off;                // (4^depth - 1)/3 : heap index of the first leaf-level node
     const float4* ntab;          // [nodes] (n_ab, n_bc, n_ca, -)
     const double4* ntab_d;       // same in fp64 (msm_locate, precise paths)
+    const float4* mtab;          // [nodes incl. leaf level] multipliers applied on ENTERING a node from its parent:
+                                 // corner-a child (1,nab,nca) | corner-b (nab,1,nbc) | corner-c (nca,nbc,1) | centre (nbc,nca,nab)
+};
+
+// Per-level "hint" tables (ico_hierarchy.h build_hint_level): the faces of one intermediate level h act as local
+// coordinate frames.  A control point's whole patch lives within a few faces of the level-h face under the control
+// point, so samples are expressed in that face's corner basis (precisely: offsets from the control point are small
+// numbers), walked across edges where needed, and only the remaining depth-h levels are descended.
+struct HintDev {
+    int h;                  // hint level
+    int nf_per_base;        // 4^h
+    int node_off;           // (4^h - 1)/3
+    const double* hdual;    // [20*4^h][9]
+    const int* hnbr;        // [20*4^h][3]
+    const float* hT;        // [20*4^h][3][9]
 };
 
 // 20 base faces: dual basis rows (alpha = A.p, beta = B.p, gamma = C.p) and centre directions.
@@ -80,6 +95,43 @@ __device__ __forceinline__ int ico_descend(const IcoDev& ico, int base, T& al, T
     return base * ico.nleaf_per_base + (n - ico.leaf_off);
 }
 
+// Descent of `nlev` levels starting at heap node n (fp32): returns the heap node reached.
+// Branch-free: the child is picked from the signs of (2x - s), the child's incoming multipliers come from one
+// 16-byte table read, and the value entering each product is |2x - s| for the child's own corner / the centre child
+// and x otherwise.
+__device__ __forceinline__ int ico_descend_from(const float4* __restrict__ mtab, int nlev, int n, float& al, float& be, float& ga) {
+#pragma unroll 1
+    for (int l = 0; l < nlev; l++) {
+        const float s = al + be + ga;
+        const float sa = fmaf(al, 2.f, -s), sb = fmaf(be, 2.f, -s), sc = fmaf(ga, 2.f, -s);
+        const bool ca = sa > 0.f, cb = !ca && sb > 0.f, cc = !ca && !cb && sc > 0.f;
+        const int child = ca ? 0 : (cb ? 1 : (cc ? 2 : 3));
+        n = 4 * n + 1 + child;
+        const float4 m = __ldg(mtab + n);
+        const float va = (cb | cc) ? al : fabsf(sa);
+        const float vb = (ca | cc) ? be : fabsf(sb);
+        const float vc = (ca | cb) ? ga : fabsf(sc);
+        al = va * m.x; be = vb * m.y; ga = vc * m.z;
+    }
+    return n;
+}
+
+// Visibility walk on the level-h faces: cross the edge opposite the most negative corner coordinate.
+__device__ __forceinline__ int ico_walk(const HintDev& hd, int face, float& al, float& be, float& ga) {
+    for (int it = 0; it < 64; it++) {
+        const float mn = fminf(al, fminf(be, ga));
+        if (mn >= 0.f) break;
+        const int e = (al == mn) ? 0 : ((be == mn) ? 1 : 2);
+        const float* T = hd.hT + ((size_t)face * 3 + e) * 9;
+        const float x = __ldg(T + 0) * al + __ldg(T + 1) * be + __ldg(T + 2) * ga;
+        const float y = __ldg(T + 3) * al + __ldg(T + 4) * be + __ldg(T + 5) * ga;
+        const float z = __ldg(T + 6) * al + __ldg(T + 7) * be + __ldg(T + 8) * ga;
+        face = __ldg(hd.hnbr + face * 3 + e);
+        al = x; be = y; ga = z;
+    }
+    return face;
+}
+
 // Full location: hint base face first (all samples of one control point's patch almost always share it).
 template <typename T>
 __device__ __forceinline__ int ico_locate(const IcoDev& ico, int hint_base, T px, T py, T pz, T& al, T& be, T& ga) {
@@ -103,12 +155,15 @@ __device__ __forceinline__ int ico_locate(const IcoDev& ico, int hint_base, T px
 // Minimal (Rodrigues) rotation taking direction a onto direction b, returned as K = R - I, fp64.
 // Restates estimate_rotation_matrix ([EXT] A2): identity below 1e-8 rad.
 __device__ __forceinline__ void rodrigues_minus_identity(const double a_[3], const double b_[3], double K[9]) {
-    double na = rsqrt(a_[0] * a_[0] + a_[1] * a_[1] + a_[2] * a_[2]);
-    double nb = rsqrt(b_[0] * b_[0] + b_[1] * b_[1] + b_[2] * b_[2]);
-    double a[3] = {a_[0] * na, a_[1] * na, a_[2] * na}, b[3] = {b_[0] * nb, b_[1] * nb, b_[2] * nb};
+    double na = sqrt(a_[0] * a_[0] + a_[1] * a_[1] + a_[2] * a_[2]);
+    double nb = sqrt(b_[0] * b_[0] + b_[1] * b_[1] + b_[2] * b_[2]);
+    double a[3] = {a_[0] / na, a_[1] / na, a_[2] / na}, b[3] = {b_[0] / nb, b_[1] / nb, b_[2] / nb};
     double c = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
     c = fmin(1.0, fmax(-1.0, c));
-    double k[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    // no FMA contraction here: for exactly (anti)parallel directions the cross product must be exactly zero, as in the
+    // reference's plain C++ (the antipode of the label-grid centre is such a control point on a regular icosphere)
+    double k[3] = {__dsub_rn(__dmul_rn(a[1], b[2]), __dmul_rn(a[2], b[1])), __dsub_rn(__dmul_rn(a[2], b[0]), __dmul_rn(a[0], b[2])),
+                   __dsub_rn(__dmul_rn(a[0], b[1]), __dmul_rn(a[1], b[0]))};
     double s = sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);  // sin(theta), well conditioned for small theta
     double theta = atan2(s, c);
 #pragma unroll

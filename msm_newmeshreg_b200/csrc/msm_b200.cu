@@ -69,8 +69,11 @@ struct msm_ctx {
     IcoHierarchy ico;
     bool have_target = false;
     int Vt = 0, Ft = 0, Ct = 0;
-    DevBuf d_ntab, d_ntab_d, d_leaf_vid, d_leaf_user, d_leaf_perm, d_tfeat, d_face_feat;
+    DevBuf d_ntab, d_ntab_d, d_mtab, d_leaf_vid, d_leaf_user, d_leaf_perm, d_tfeat, d_face_feat;
     int face_feat_cq = -1;  // layout the face-packed features were built for (-1 none, 0 univariate, q quads)
+    int hint_level = -1;    // level the hint tables below were built for
+    DevBuf d_hdual, d_hnbr, d_hT;
+    double max_label_disp = 0.0;  // max |label - centre| (sizes the hint level)
 
     // source
     int Vs = 0, Cs = 0, wrows = 0;
@@ -101,6 +104,7 @@ struct msm_ctx {
     int maxP = 0;
     DevBuf d_counts, d_off, d_idx, d_unc, d_unc_count, d_acc_off, d_acc_idx, d_totmax;
     DevBuf d_px, d_py, d_pz, d_pa, d_pw;
+    DevBuf d_pcx, d_pcy, d_pcz, d_hint_face, d_lab12, d_tref;  // k_unary_setup outputs
     int pack_cp = 0;
 
     // outputs / scratch
@@ -190,6 +194,7 @@ IcoDev ico_dev(const msm_ctx* ctx) {
     d.leaf_off = (d.nleaf_per_base - 1) / 3;
     d.ntab = ctx->d_ntab.as<float4>();
     d.ntab_d = ctx->d_ntab_d.as<double4>();
+    d.mtab = ctx->d_mtab.as<float4>();
     return d;
 }
 
@@ -219,10 +224,54 @@ int ensure_face_feat(msm_ctx* ctx) {
     const size_t per_face = want == 0 ? 4 : (size_t)3 * Cp;
     CK(ctx->d_face_feat.ensure((size_t)ctx->Ft * per_face * sizeof(float)));
     k_face_pack<<<(ctx->Ft + 255) / 256, 256, 0, ctx->stream>>>(ctx->Ft, ctx->Ct, Cp, ctx->Vt, want == 0 ? 1 : 0, ctx->d_leaf_vid.as<int>(),
-                                                               ctx->d_tfeat.as<float>(), ctx->d_face_feat.as<float>());
+                                                               ctx->d_tfeat.as<double>(), ctx->d_face_feat.as<float>());
     KLAUNCH_CHECK();
     ctx->face_feat_cq = want;
     return 0;
+}
+
+// Hint level: the deepest level whose faces are still comfortably larger than the disc a control point's patch
+// sweeps under all labels (patch radius + largest label displacement); few edge walks, few levels left to descend.
+int choose_hint_level(const msm_ctx* ctx) {
+    const int depth = ctx->ico.depth;
+    if (depth <= 0) return 0;
+    if (const char* e = getenv("MSM_HINT_LEVEL")) {
+        int h = atoi(e);
+        return std::max(0, std::min(depth - 1, h));
+    }
+    double maxsep = 0.0;
+    for (double v : ctx->h_maxsep) maxsep = std::max(maxsep, v);
+    const double disc = ctx->par.range * maxsep + ctx->max_label_disp;
+    const double edge0 = 110.71487177940904;  // icosahedron edge arc length at R = 100
+    int h = 0;
+    while (h + 1 < depth && edge0 / double(1 << (h + 1)) > 3.0 * disc) h++;
+    return h;
+}
+
+int ensure_hint_level(msm_ctx* ctx) {
+    const int h = choose_hint_level(ctx);
+    if (h == ctx->hint_level) return 0;
+    std::vector<double> hdual, hT;
+    std::vector<int> hnbr;
+    ctx->ico.build_hint_level(h, hdual, hnbr, hT);
+    std::vector<float> hTf(hT.begin(), hT.end());
+    if (upload(ctx, ctx->d_hdual, hdual.data(), hdual.size())) return 1;
+    if (upload(ctx, ctx->d_hnbr, hnbr.data(), hnbr.size())) return 1;
+    if (upload(ctx, ctx->d_hT, hTf.data(), hTf.size())) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hint_level = h;
+    return 0;
+}
+
+HintDev hint_dev(const msm_ctx* ctx) {
+    HintDev d;
+    d.h = ctx->hint_level;
+    d.nf_per_base = 1 << (2 * d.h);
+    d.node_off = (d.nf_per_base - 1) / 3;
+    d.hdual = ctx->d_hdual.as<double>();
+    d.hnbr = ctx->d_hnbr.as<int>();
+    d.hT = ctx->d_hT.as<float>();
+    return d;
 }
 
 TripArgs trip_args(msm_ctx* ctx) {
@@ -325,6 +374,7 @@ int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int 
     CK(cudaSetDevice(ctx->device));
     ctx->have_target = false;
     ctx->face_feat_cq = -1;
+    ctx->hint_level = -1;
     if (!ctx->ico.build(xyz, V, tris, F)) FAIL("msm_set_target: " + ctx->ico.error);
     const IcoHierarchy& H = ctx->ico;
     ctx->Vt = V; ctx->Ft = F; ctx->Ct = feat ? C : 0;
@@ -337,6 +387,16 @@ int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int 
             for (int j = 0; j < 3; j++) { nf[4 * i + j] = (float)H.ntab[i][j]; nd[4 * i + j] = H.ntab[i][j]; }
         if (upload(ctx, ctx->d_ntab, nf.data(), nf.size())) return 1;
         if (upload(ctx, ctx->d_ntab_d, nd.data(), nd.size())) return 1;
+        // child-indexed multiplier table (all nodes of levels 0..depth; node 0 unused)
+        const size_t nall = ((size_t(1) << (2 * (H.depth + 1))) - 1) / 3;
+        std::vector<float> mt(nall * 4, 1.f);
+        for (size_t n = 0; n < H.ntab.size(); n++) {
+            const float nab = (float)H.ntab[n][0], nbc = (float)H.ntab[n][1], nca = (float)H.ntab[n][2];
+            const float mul[4][3] = {{1.f, nab, nca}, {nab, 1.f, nbc}, {nca, nbc, 1.f}, {nbc, nca, nab}};
+            for (int c = 0; c < 4; c++)
+                for (int j = 0; j < 3; j++) mt[(4 * n + 1 + c) * 4 + j] = mul[c][j];
+        }
+        if (upload(ctx, ctx->d_mtab, mt.data(), mt.size())) return 1;
         CK(cudaStreamSynchronize(ctx->stream));
     }
     {
@@ -366,7 +426,8 @@ int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int 
     }
     if (feat) {
         if (C <= 0) FAIL("msm_set_target: C must be positive");
-        if (upload_as_float(ctx, ctx->d_tfeat, feat, (size_t)C * V)) return 1;
+        if (upload(ctx, ctx->d_tfeat, feat, (size_t)C * V)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->have_target = true;
     return 0;
@@ -378,7 +439,8 @@ int msm_set_source(msm_ctx* ctx, const double* xyz, int V, const double* feat, i
     if (wrows != 0 && wrows != 1 && wrows != C)
         FAIL("DiscreteModel ERROR:: costfunction weighting has dimensions incompatible with data");  // :116-117
     ctx->Vs = V; ctx->Cs = C; ctx->wrows = wrows; ctx->multivariate = multivariate != 0;
-    if (upload_as_float(ctx, ctx->d_sfeat, feat, (size_t)C * V)) return 1;
+    if (upload(ctx, ctx->d_sfeat, feat, (size_t)C * V)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
     if (wrows > 0 && upload_as_float(ctx, ctx->d_swgt, cfweight, (size_t)wrows * V)) return 1;
     ctx->have_patches = false;
     return msm_reset_source(ctx, xyz);
@@ -458,6 +520,11 @@ int msm_set_labels(msm_ctx* ctx, const double* labels, int L, const double* cent
     if (L <= 0) FAIL("msm_set_labels: empty label set");
     ctx->L = L;
     for (int j = 0; j < 3; j++) ctx->centre[j] = centre[j];
+    ctx->max_label_disp = 0.0;
+    for (int l = 0; l < L; l++) {
+        const double dx = labels[3 * l] - centre[0], dy = labels[3 * l + 1] - centre[1], dz = labels[3 * l + 2] - centre[2];
+        ctx->max_label_disp = std::max(ctx->max_label_disp, std::sqrt(dx * dx + dy * dy + dz * dz));
+    }
     if (upload(ctx, ctx->d_labels, labels, (size_t)L * 3)) return 1;
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->rot_dirty = true;
@@ -568,10 +635,10 @@ int msm_build_patches(msm_ctx* ctx) {
     CK(ctx->d_px.ensure(tot * 4)); CK(ctx->d_py.ensure(tot * 4)); CK(ctx->d_pz.ensure(tot * 4));
     CK(ctx->d_pa.ensure(tot * 4 * Cp)); CK(ctx->d_pw.ensure(tot * 4 * Cp));
     if (ctx->total > 0) {
-        k_patch_pack<<<(unsigned)((ctx->total + 255) / 256), 256, 0, ctx->stream>>>(
-            (int)ctx->total, Cp, ctx->Cs, ctx->wrows, ctx->Vs, ctx->d_idx.as<int>(), ctx->d_sxf.as<float>(), ctx->d_syf.as<float>(),
-            ctx->d_szf.as<float>(), ctx->d_sfeat.as<float>(), ctx->d_swgt.as<float>(), ctx->d_px.as<float>(), ctx->d_py.as<float>(),
-            ctx->d_pz.as<float>(), ctx->d_pa.as<float>(), ctx->d_pw.as<float>());
+        k_patch_pack<<<Ns, 128, 0, ctx->stream>>>(ctx->k_begin, (int)ctx->total, Cp, ctx->Cs, ctx->wrows, ctx->Vs, ctx->multivariate ? 0 : 1,
+                                                 ctx->d_off.as<int>(), ctx->d_idx.as<int>(), ctx->d_src.as<double>(), ctx->d_cp.as<double>(),
+                                                 ctx->d_sfeat.as<double>(), ctx->d_swgt.as<float>(), ctx->d_px.as<float>(),
+                                                 ctx->d_py.as<float>(), ctx->d_pz.as<float>(), ctx->d_pa.as<float>(), ctx->d_pw.as<float>());
         KLAUNCH_CHECK();
     }
     ctx->have_patches = true;
@@ -609,13 +676,14 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
     if (ctx->Ct != ctx->Cs) FAIL("source and target feature dimensions differ");
     if (ensure_label_rot(ctx)) return 1;
     if (ensure_face_feat(ctx)) return 1;
+    if (ensure_hint_level(ctx)) return 1;
     const int Ns = ctx->k_end - ctx->k_begin;
     if (Ns == 0) return 0;
     const int CQ = ctx->face_feat_cq;
     const int Cp = CQ == 0 ? 1 : 4 * CQ;
     const int L = ctx->L, Pmax = std::max(ctx->maxP, 1);
     // label groups: fit shared memory (<= ~56 KB so several CTAs share an SM) and expose >= 4 CTAs per SM
-    auto smem_for = [&](int Lg) { return (size_t)4 * ((size_t)(3 + 2 * Cp) * Pmax + (size_t)Lg * 12 + (size_t)Lg * Pmax); };
+    auto smem_for = [&](int Lg) { return (size_t)4 * ((size_t)(6 + 2 * Cp) * Pmax + (size_t)Lg * 12 + (size_t)Lg * Pmax); };
     int Lg = L;
     while (Lg > 1 && smem_for(Lg) > 56 * 1024) Lg--;
     const int want_ctas = 4 * 148;
@@ -631,15 +699,34 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
     a.px = ctx->d_px.as<float>(); a.py = ctx->d_py.as<float>(); a.pz = ctx->d_pz.as<float>();
     a.pa = ctx->d_pa.as<float>(); a.pw = ctx->d_pw.as<float>();
     a.total = (int)ctx->total;
-    a.Kf = ctx->d_Kf.as<float>();
-    a.cp = ctx->d_cp.as<double>();
+    a.hint = hint_dev(ctx);
     a.absw = ctx->d_absw.as<float>();
     a.face_feat = ctx->d_face_feat.as<float>();
     a.ico = ico_dev(ctx);
     a.simmeasure = ctx->par.simmeasure;
     a.out = d_out;
+    const size_t tot = std::max<long long>(ctx->total, 1);
+    CK(ctx->d_pcx.ensure(tot * 4)); CK(ctx->d_pcy.ensure(tot * 4)); CK(ctx->d_pcz.ensure(tot * 4));
+    CK(ctx->d_hint_face.ensure((size_t)Ns * 4));
+    CK(ctx->d_lab12.ensure((size_t)Ns * L * 12 * 4));
+    CK(ctx->d_tref.ensure((size_t)Ns * 4));
+    a.pcx = ctx->d_pcx.as<float>(); a.pcy = ctx->d_pcy.as<float>(); a.pcz = ctx->d_pcz.as<float>();
+    a.tref = ctx->d_tref.as<float>();
+    a.hint_face = ctx->d_hint_face.as<int>();
+    a.lab12 = ctx->d_lab12.as<float>();
     const unsigned grid = (unsigned)((long long)Ns * a.G);
     Timer tm(ctx, "unary");
+    {
+        UnarySetupArgs s;
+        s.k_begin = ctx->k_begin; s.L = L; s.off = a.off; s.px = a.px; s.py = a.py; s.pz = a.pz;
+        s.Kd = ctx->d_Kd.as<double>(); s.cp = ctx->d_cp.as<double>(); s.ico = a.ico; s.hint = a.hint;
+        s.hint_face = ctx->d_hint_face.as<int>(); s.lab12 = ctx->d_lab12.as<float>();
+        s.tref = ctx->d_tref.as<float>();
+        s.face_feat = CQ == 0 ? ctx->d_face_feat.as<float>() : nullptr;
+        s.pcx = ctx->d_pcx.as<float>(); s.pcy = ctx->d_pcy.as<float>(); s.pcz = ctx->d_pcz.as<float>();
+        k_unary_setup<<<Ns, 128, 0, ctx->stream>>>(s);
+        KLAUNCH_CHECK();
+    }
 #define LAUNCH_UNARY(Q)                                                                                             \
     do {                                                                                                            \
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_unary<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -1,0 +1,264 @@
+// unary.cuh — the unary data term (src/DiscreteCostFunction.cpp:306-313,412-448,483-526; similarities.cc:122-173).
+//
+// k_unary_setup (fp64, one CTA per control point k): the level-h "hint" face under CP_k, CP_k's corner coordinates in
+//   it, and from those
+//     per sample i :  c_i = x(CP_k) + A r_i           (r_i = SRC_i - CP_k, the packed offsets)
+//     per label  l :  M_l = A (R_kl - I),  g_l = A (R_kl - I) CP_k
+//   where A is the dual basis of the hint face (x = A p are the coordinates of p in the face's corner basis); plus
+//   tref_k = target feature under CP_k (Pearson correlation is shift invariant: the univariate kernel works on
+//   target values relative to tref_k and source values relative to the patch's first sample, so that fp32 storage
+//   resolves the small variation inside a patch instead of the field's absolute level).
+// k_unary (fp32, one CTA per (control point, label group)):
+//   Phase 1: stage the patch (r, c, source features, weights) and the label tables in shared memory — all coalesced.
+//   Phase 2: every thread takes (label, sample) items.  Corner coordinates of the rotated sample R_kl (CP_k + r_i):
+//            x = c_i + g_l + M_l r_i   (12 FMA), edge walk on level h where a coordinate is negative (rare: the hint
+//            level is chosen so that a face is much larger than a patch), branch-free 4-way scalar descent of the
+//            remaining levels, ONE 16-byte gather of the face-packed target features, interpolation.
+//   Phase 3: 8 lanes per label reduce the weighted Pearson moments (fp64 accumulators, fixed order => deterministic).
+// CQ = number of float4 channel quads of the multivariate cost function (0 = univariate).
+#pragma once
+#include "locate.cuh"
+
+namespace msm {
+
+// fp64 descent of a point from its base face: `nlev` levels; returns base face, heap node, corner coordinates
+__device__ __forceinline__ void descend_d(const IcoDev& ico, int nlev, double px, double py, double pz, int& base, int& n, double& al,
+                                          double& be, double& ga) {
+    base = ico_base_face<double>(px, py, pz);
+    const double* d = c_ico_base.dual_d[base];
+    al = d[0] * px + d[1] * py + d[2] * pz; be = d[3] * px + d[4] * py + d[5] * pz; ga = d[6] * px + d[7] * py + d[8] * pz;
+    n = 0;
+    for (int l = 0; l < nlev; l++) {
+        const double4 nn = ico.ntab_d[n];
+        const double s = al + be + ga;
+        const double sa = (al + al) - s, sb = (be + be) - s, sc = (ga + ga) - s;
+        int child; double x, y, z;
+        if (sa > 0.0) { child = 0; x = sa; y = be * nn.x; z = ga * nn.z; }
+        else if (sb > 0.0) { child = 1; x = al * nn.x; y = sb; z = ga * nn.y; }
+        else if (sc > 0.0) { child = 2; x = al * nn.z; y = be * nn.y; z = sc; }
+        else { child = 3; x = -sa * nn.y; y = -sb * nn.z; z = -sc * nn.x; }
+        al = x; be = y; ga = z;
+        n = 4 * n + 1 + child;
+    }
+}
+
+struct UnarySetupArgs {
+    int k_begin, L;
+    const int* off;                     // [Ns+1]
+    const float* px; const float* py; const float* pz;  // packed offsets r
+    const double* Kd;                   // [N][L][9]  R_kl - I
+    const double* cp;                   // [N][3]
+    const float* face_feat;             // univariate face-packed features (tref) or nullptr
+    IcoDev ico;
+    HintDev hint;
+    int* hint_face;                     // [Ns]
+    float* tref;                        // [Ns]
+    float* lab12;                       // [Ns][L][12] : M (9) then g (3)
+    float* pcx; float* pcy; float* pcz; // [total] corner coordinates of the unrotated samples
+};
+
+__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a) {
+    const int row = blockIdx.x, k = a.k_begin + row, tid = threadIdx.x;
+    __shared__ double A[9], x0[3];
+    const double ox = a.cp[3 * k], oy = a.cp[3 * k + 1], oz = a.cp[3 * k + 2];
+    if (tid == 0) {
+        int base, n; double al, be, ga;
+        descend_d(a.ico, a.hint.h, ox, oy, oz, base, n, al, be, ga);
+        const int f = base * a.hint.nf_per_base + (n - a.hint.node_off);
+        a.hint_face[row] = f;
+        const double* Ag = a.hint.hdual + (size_t)f * 9;
+#pragma unroll
+        for (int i = 0; i < 9; i++) A[i] = Ag[i];
+        x0[0] = Ag[0] * ox + Ag[1] * oy + Ag[2] * oz;
+        x0[1] = Ag[3] * ox + Ag[4] * oy + Ag[5] * oz;
+        x0[2] = Ag[6] * ox + Ag[7] * oy + Ag[8] * oz;
+    }
+    if (tid == 32) {
+        float tr = 0.f;
+        if (a.face_feat) {
+            int base, n; double al, be, ga;
+            descend_d(a.ico, a.ico.depth, ox, oy, oz, base, n, al, be, ga);
+            tr = reinterpret_cast<const float4*>(a.face_feat)[base * a.ico.nleaf_per_base + (n - a.ico.leaf_off)].x;
+        }
+        a.tref[row] = tr;
+    }
+    __syncthreads();
+    for (int s = a.off[row] + tid; s < a.off[row + 1]; s += 128) {
+        const double x = a.px[s], y = a.py[s], z = a.pz[s];
+        a.pcx[s] = (float)(x0[0] + (A[0] * x + A[1] * y + A[2] * z));
+        a.pcy[s] = (float)(x0[1] + (A[3] * x + A[4] * y + A[5] * z));
+        a.pcz[s] = (float)(x0[2] + (A[6] * x + A[7] * y + A[8] * z));
+    }
+    for (int l = tid; l < a.L; l += 128) {
+        const double* K = a.Kd + ((size_t)k * a.L + l) * 9;
+        // the control point itself moves by (R-I) CP_k (no cancellation: K holds R-I at full precision)
+        const double dx = K[0] * ox + K[1] * oy + K[2] * oz, dy = K[3] * ox + K[4] * oy + K[5] * oz, dz = K[6] * ox + K[7] * oy + K[8] * oz;
+        float* o = a.lab12 + ((size_t)row * a.L + l) * 12;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const double A0 = A[3 * r], A1 = A[3 * r + 1], A2 = A[3 * r + 2];
+            o[3 * r + 0] = (float)(A0 * K[0] + A1 * K[3] + A2 * K[6]);
+            o[3 * r + 1] = (float)(A0 * K[1] + A1 * K[4] + A2 * K[7]);
+            o[3 * r + 2] = (float)(A0 * K[2] + A1 * K[5] + A2 * K[8]);
+            o[9 + r] = (float)(A0 * dx + A1 * dy + A2 * dz);
+        }
+    }
+}
+
+struct UnaryArgs {
+    int k_begin, Ns, L, G, Lg;          // shard rows, labels, label groups, labels per group
+    const int* off;                     // [Ns+1]
+    const float* px; const float* py; const float* pz;     // packed offsets r = SRC - CP_k
+    const float* pcx; const float* pcy; const float* pcz;  // corner coordinates c
+    const float* pa; const float* pw;   // packed source features / weights [Cp][total]
+    int total;                          // stride of pa/pw channels
+    const int* hint_face;               // [Ns]
+    const float* tref;                  // [Ns]
+    const float* lab12;                 // [Ns][L][12]
+    const float* absw;                  // [N]
+    const float* face_feat;             // face-packed target features
+    IcoDev ico;
+    HintDev hint;
+    int simmeasure;
+    float* out;                         // [L][Ns]
+};
+
+__device__ __forceinline__ double group8_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+template <int CQ>
+__global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
+    constexpr int CP_ = CQ == 0 ? 1 : 4 * CQ;  // padded channel count
+    extern __shared__ float smem[];
+    const int row = blockIdx.x / a.G, g = blockIdx.x - row * a.G;
+    const int k = a.k_begin + row;
+    const int l0 = g * a.Lg, l1 = min(a.L, l0 + a.Lg), nl = l1 - l0;
+    const int s0 = a.off[row], P = a.off[row + 1] - s0;
+    const int tid = threadIdx.x;
+    // smem carve: r[3][P] | c[3][P] | a[CP_][P] | w[CP_][P] | lab[Lg][12] | tbuf[Lg][P]
+    float* rx = smem; float* ry = rx + P; float* rz = ry + P;
+    float* cx = rz + P; float* cy = cx + P; float* cz = cy + P;
+    float* sa = cz + P; float* sw = sa + CP_ * P;
+    float* sK = sw + CP_ * P;
+    float* tb = sK + a.Lg * 12;
+
+    for (int i = tid; i < P; i += 256) {
+        rx[i] = a.px[s0 + i]; ry[i] = a.py[s0 + i]; rz[i] = a.pz[s0 + i];
+        cx[i] = a.pcx[s0 + i]; cy[i] = a.pcy[s0 + i]; cz[i] = a.pcz[s0 + i];
+#pragma unroll
+        for (int c = 0; c < CP_; c++) {
+            sa[c * P + i] = a.pa[(size_t)c * a.total + s0 + i];
+            sw[c * P + i] = a.pw[(size_t)c * a.total + s0 + i];
+        }
+    }
+    for (int i = tid; i < nl * 12; i += 256) sK[i] = a.lab12[((size_t)row * a.L + l0) * 12 + i];
+    const int face0 = a.hint_face[row];
+    const float tref = a.tref[row];
+    __syncthreads();
+    const int items = nl * P;
+    const float invP = 1.0f / (float)max(P, 1);
+    const int hshift = 2 * a.hint.h;
+    const int nlev = a.ico.depth - a.hint.h;
+    const float4* __restrict__ mtab = a.ico.mtab;
+    const int leaf_off = a.ico.leaf_off, nleaf = a.ico.nleaf_per_base, node_off = a.hint.node_off;
+
+    for (int j = tid; j < items; j += 256) {
+        const int l = (int)(((float)j + 0.5f) * invP);
+        const int i = j - l * P;
+        const float x = rx[i], y = ry[i], z = rz[i];
+        const float* M = sK + l * 12;
+        float al = cx[i] + (M[9] + (M[0] * x + M[1] * y + M[2] * z));
+        float be = cy[i] + (M[10] + (M[3] * x + M[4] * y + M[5] * z));
+        float ga = cz[i] + (M[11] + (M[6] * x + M[7] * y + M[8] * z));
+        int face = face0;
+        if (fminf(al, fminf(be, ga)) < 0.f) face = ico_walk(a.hint, face0, al, be, ga);
+        const int base = face >> hshift;
+        const int n = ico_descend_from(mtab, nlev, node_off + (face - (base << hshift)), al, be, ga);
+        const int leaf = base * nleaf + (n - leaf_off);
+        const float inv = 1.0f / (al + be + ga);
+        if (CQ == 0) {
+            // face-packed (f0_hi, f0_lo, f1-f0, f2-f0): t - tref = (f0_hi - tref) + f0_lo + wb (f1-f0) + wc (f2-f0)
+            const float4 f = __ldg(reinterpret_cast<const float4*>(a.face_feat) + leaf);
+            tb[j] = ((f.x - tref) + f.y) + ((be * inv) * f.z + (ga * inv) * f.w);
+        } else {
+            // multivariate: Pearson across the channels of this one sample (src/DiscreteCostFunction.cpp:515-518)
+            const float4* ff = reinterpret_cast<const float4*>(a.face_feat) + (size_t)leaf * 3 * CQ;
+            float t[CP_];
+            const float wa = al * inv, wb = be * inv, wc = ga * inv;
+#pragma unroll
+            for (int q = 0; q < CQ; q++) {
+                const float4 f0 = __ldg(ff + q), f1 = __ldg(ff + CQ + q), f2 = __ldg(ff + 2 * CQ + q);
+                t[4 * q + 0] = wa * f0.x + wb * f1.x + wc * f2.x;
+                t[4 * q + 1] = wa * f0.y + wb * f1.y + wc * f2.y;
+                t[4 * q + 2] = wa * f0.z + wb * f1.z + wc * f2.z;
+                t[4 * q + 3] = wa * f0.w + wb * f1.w + wc * f2.w;
+            }
+            float W = 0.f, Sa = 0.f, St = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP_; c++) {
+                const float w = sw[c * P + i];
+                W += w; Sa += w * sa[c * P + i]; St += w * t[c];
+            }
+            if (W > 0.f) { Sa /= W; St /= W; }
+            float pr = 0.f, va = 0.f, vt = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP_; c++) {
+                const float w = sw[c * P + i];
+                const float da = sa[c * P + i] - Sa, dt = t[c] - St;
+                pr += w * da * dt; va += w * da * da; vt += w * dt * dt;
+            }
+            if (W > 0.f) { pr /= W; va /= W; vt /= W; }
+            const float rho = (va == 0.f || vt == 0.f) ? 0.f : pr / (sqrtf(va) * sqrtf(vt));
+            tb[j] = 1.0f - (1.0f + rho) * 0.5f;
+        }
+    }
+    __syncthreads();
+
+    // Phase 3: 8 lanes per label.
+    const float AW = a.absw[k];
+    const bool pos = (a.simmeasure == 1 || a.simmeasure == 2);
+    const int grp = tid >> 3, sub = tid & 7;
+    for (int lb = 0; lb < nl; lb += 32) {   // warp-uniform trip count
+        const int l = lb + grp;
+        const bool act = l < nl;
+        const float* t = tb + (act ? l : 0) * P;
+        double cost;
+        if (CQ == 0) {
+            // weighted Pearson (src/similarities.cc:122-173) from single-pass moments of the SHIFTED data
+            double W = 0, Sa = 0, Saa = 0, St = 0, Stt = 0, Sat = 0;
+            if (act)
+                for (int i = sub; i < P; i += 8) {
+                    const double w = sw[i], av = sa[i], tv = t[i];
+                    const double wa = w * av, wt = w * tv;
+                    W += w; Sa += wa; St += wt; Saa += wa * av; Stt += wt * tv; Sat += wa * tv;
+                }
+            W = group8_sum(W); Sa = group8_sum(Sa); St = group8_sum(St);
+            Saa = group8_sum(Saa); Stt = group8_sum(Stt); Sat = group8_sum(Sat);
+            double ma = Sa, mt = St;                       // :139-142 means are divided only when sum > 0
+            if (W > 0) { const double iw = 1.0 / W; ma *= iw; mt *= iw; }
+            double pr = Sat - ma * St - mt * Sa + ma * mt * W;   // = sum w (a-ma)(t-mt)
+            double va = Saa - 2.0 * ma * Sa + ma * ma * W;
+            double vt = Stt - 2.0 * mt * St + mt * mt * W;
+            // (the common 1/W of :164-169 cancels in the ratio)
+            // :171 "either variance is zero -> 0": a variance below 1e-14 of the raw second moment is rounding noise
+            double rho = 0.0;
+            if (va > 1e-14 * Saa && vt > 1e-14 * Stt) rho = pr * rsqrt(va) * rsqrt(vt);
+            cost = (double)AW * (1.0 - (1.0 + rho) * 0.5);
+        } else {
+            double s = 0;
+            if (act)
+                for (int i = sub; i < P; i += 8) s += (double)t[i];
+            s = group8_sum(s);
+            if (P > 0) s /= (double)P;
+            cost = (double)AW * s;
+        }
+        if (!pos) cost = -cost;
+        if (act && sub == 0) a.out[(size_t)(l0 + l) * a.Ns + row] = (float)cost;
+    }
+}
+
+}  // namespace msm
