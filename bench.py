@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native newMSM cost-evaluation path.
+
+Metric (BASELINE.json): unary + triplet cost evaluations per second (one evaluation = one control point x label unary
+cost, or one triplet x label-triple cost).
+
+Workload (config.workload): C3 of BASELINE.json — ico7 data mesh (163 842 vertices) x ico5 control grid (10 242 control
+points, 20 480 triplets), L = 19 labels, range 1, univariate NCC/Pearson.  One "step" is one outer iteration's cost
+evaluation for B independent subject->template registrations per GPU: the whole unary table (N*L evaluations) plus the
+fusion-move triplet costs of every label (L*T*8 evaluations) per subject.  Subjects are independent, so N GPUs process
+N*B subjects with no data-path collective ("weak" scaling, SURVEY.md §8e row "batched").  B subjects x ~80 MB of device
+state exceed the 126 MB L2, so successive timed iterations do not find their inputs in L2.
+
+  value : evaluations / second, inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks.
+  e2e   : the same step through the reference-facing host classes (NonLinearSRegDiscreteModel::reset_meshspace ->
+          setupCostFunction [patch construction + unary table] -> triplet moves) with pinned HOST buffers in and out.
+  --impl reference : the oracle's CPU restatement of the reference path on the host cores, bounded sample of the same
+          workload (the reference itself needs FSL and cannot be built: SURVEY.md §0.2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0
+RAD = 100.0
+
+
+def f32(x):
+    return float(np.float32(x))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------- synthetic data
+def random_field(xyz, seed, nwaves=32, kmax=6.0):
+    rng = np.random.default_rng(seed)
+    u = xyz / RAD
+    k = rng.normal(size=(nwaves, 3))
+    k *= (rng.uniform(1.0, kmax, size=(nwaves, 1)) / np.linalg.norm(k, axis=1, keepdims=True))
+    f = (rng.normal(size=nwaves)[None, :] * np.cos(u @ k.T + rng.uniform(0, 2 * np.pi, size=nwaves)[None, :])).sum(1)
+    return (f - f.mean()) / f.std()
+
+
+def smooth_warp(xyz, seed, amplitude):
+    rng = np.random.default_rng(seed)
+    u = xyz / RAD
+    d = np.zeros_like(u)
+    for _ in range(6):
+        k = rng.normal(size=3) * 2.0
+        d += rng.normal(size=3)[None, :] * np.sin(u @ k + rng.uniform(0, 2 * np.pi))[:, None]
+    d -= (d * u).sum(1, keepdims=True) * u
+    d *= amplitude / max(np.abs(d).max(), 1e-12)
+    p = xyz + d
+    return p * (RAD / np.linalg.norm(p, axis=1, keepdims=True))
+
+
+def rotate(xyz, axis, deg):
+    axis = np.asarray(axis, float); axis /= np.linalg.norm(axis)
+    t = np.deg2rad(deg)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return xyz @ (np.eye(3) + np.sin(t) * K + (1 - np.cos(t)) * K @ K).T
+
+
+PARAMS = dict(lam=f32(0.1), rexp=f32(2.0), mu=f32(0.4), kappa=f32(1.6), k_exp=f32(2.0), rng=f32(1.0), simmeasure=2, rmode=3)
+
+
+class Subject:
+    """Synthetic subject: reference field on the template icosphere, source field = the same random process seen through
+    a known 2-degree rotation, source mesh = the icosphere pushed through a smooth warp."""
+
+    def __init__(self, txyz, ttris, C, seed, cp_spacing):
+        self.ref = np.stack([random_field(txyz, seed * 10 + c) for c in range(C)])
+        moved = rotate(txyz, [0.3, -0.5, 0.8], 2.0)
+        self.inp = np.stack([random_field(moved, seed * 10 + c) for c in range(C)])
+        self.sxyz = smooth_warp(txyz, seed + 100, 0.3 * cp_spacing)
+
+
+# ---------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU (oracle) arm
+def oracle_sample(data_level, cp_level, C, rows, threads, seed=1000, steps=1, warmup=0):
+    """The oracle's restatement of the reference path on a bounded sample: patch construction (single thread, as in the
+    reference: src/DiscreteCostFunction.cpp:394-410 has no OpenMP), unary table (labels outer, omp over control points,
+    :306-313) for `rows` control points, and the fusion-move triplet costs of every label for the proportional share of
+    triplets (omp over triplets, include/Fusion/Fusion.h:180)."""
+    from oracle import pyorc
+    txyz, ttris = pyorc.icosphere(data_level)
+    cxyz0, ctris = pyorc.icosphere(cp_level)
+    maxsep, mvdmax, mvd = pyorc.spacings(cxyz0, ctris)
+    S = Subject(txyz, ttris, C, seed, mvd)
+    samples, bary, centre = pyorc.label_grid(cp_level + 2, 0.5 * mvdmax)
+    cxyz = smooth_warp(cxyz0, seed + 200, 0.1 * mvd)
+    trip = pyorc.triplets(cxyz0, ctris)
+    N, L, T = len(cxyz), len(bary), len(trip)
+    rows = min(rows, N)
+    tsel = np.arange(max(1, T * rows // N))
+    cf = pyorc.CostFunction()
+    cf.set_params(threads=threads, **PARAMS)
+    cf.set_meshes(txyz, ttris, S.sxyz, cxyz0, ctris)
+    cf.reset_cpgrid(cxyz); cf.set_orig(cxyz0)
+    cf.set_features(S.ref, S.inp, C > 1)
+    cf.set_spacings(maxsep, mvdmax)
+    cf.set_labels(bary, pyorc.rotations(centre, cxyz))
+    cf.set_triplets(trip)
+    lab = np.random.default_rng(7).integers(0, L, N).astype(np.int32)
+    q = np.empty((L, len(tsel), 8, 4), np.int32)
+    for a in range(L):
+        for combo in range(8):
+            q[a, :, combo, 0] = tsel
+            q[a, :, combo, 1] = np.where(combo & 4, a, lab[trip[tsel, 0]])
+            q[a, :, combo, 2] = np.where(combo & 2, a, lab[trip[tsel, 1]])
+            q[a, :, combo, 3] = np.where(combo & 1, a, lab[trip[tsel, 2]])
+    q = q.reshape(-1, 4)
+    evals = rows * L + len(q)
+    times = {"patches": [], "unary": [], "triplet": []}
+    for it in range(warmup + steps):
+        cf.set_params(threads=1, **PARAMS)
+        t0 = time.perf_counter(); cf.get_source_data(0, rows); t1 = time.perf_counter()
+        cf.set_params(threads=threads, **PARAMS)
+        cf.unary_costs(0, rows); t2 = time.perf_counter()
+        cf.triplet_costs(q); t3 = time.perf_counter()
+        if it >= warmup:
+            times["patches"].append(t1 - t0); times["unary"].append(t2 - t1); times["triplet"].append(t3 - t2)
+    tp, tu, tt = (float(np.mean(times[k])) for k in ("patches", "unary", "triplet"))
+    return dict(evals=evals, rows=rows, N=N, L=L, T=T, ntrip=len(tsel), t_patches=tp, t_unary=tu, t_triplet=tt,
+                evals_per_s_resident=evals / (tu + tt), evals_per_s_e2e=evals / (tp + tu + tt))
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--subjects-per-gpu", type=int, default=4)
+    ap.add_argument("--data-level", type=int, default=7)
+    ap.add_argument("--cp-level", type=int, default=5)
+    ap.add_argument("--channels", type=int, default=1)
+    ap.add_argument("--cpu-rows", type=int, default=1024, help="control points in the bounded CPU sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    C = args.channels
+    workload = (f"C3 (BASELINE.json configs[2]): ico{args.data_level} data x ico{args.cp_level} control grid, L=19 labels, C={C}, "
+                f"range 1, Pearson; step = unary table + all-label fusion-move triplet costs for {args.subjects_per_gpu} independent subjects per GPU")
+    metric, unit = "unary+triplet cost evals/s", "evals/s"
+
+    # ------------------------------------------------------------------ reference (CPU) arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import __graft_entry__ as g
+        try:
+            g.build_oracle()
+        except Exception as e:  # prebuilt oracle/liborc.so travels with the snapshot
+            print(f"# oracle rebuild skipped: {e}", file=sys.stderr)
+        threads = os.cpu_count() or 1
+        r = oracle_sample(args.data_level, args.cp_level, C, args.cpu_rows, threads, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+        v = r["evals_per_s_e2e"]
+        sample = (f"{r['rows']} of {r['N']} control points (patch construction 1 thread as in the reference, unary {threads} threads) + "
+                  f"{r['ntrip']} of {r['T']} triplets x {r['L']} labels x 8 moves; oracle port (reference needs FSL)")
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * (r["t_patches"] + r["t_unary"] + r["t_triplet"]), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "sample": sample},
+                "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample,
+                                 "value_tables_only": r["evals_per_s_resident"], "t_patches_s": r["t_patches"], "t_unary_s": r["t_unary"],
+                                 "t_triplet_s": r["t_triplet"]},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    os.environ["MSM_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+    if local == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from msm_newmeshreg_b200 import host
+
+    B = args.subjects_per_gpu
+    txyz, ttris = host.icosphere(args.data_level)
+    cxyz0, ctris = host.icosphere(args.cp_level)
+    edge = np.linalg.norm(cxyz0[ctris[:, 0]] - cxyz0[ctris[:, 1]], axis=1)
+    mvd = float(edge.mean())
+    # one explicit (non-default) stream for every context: the events below are recorded on the SAME stream the kernels
+    # are launched on (a NULL stream handle would make each context fall back to its own private stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    models, ctxs, subs, host_bufs = [], [], [], []
+    for s in range(B):
+        seed = 1000 + 97 * rank + s
+        S = Subject(txyz, ttris, C, seed, mvd)
+        m = host.Model(sgres=args.cp_level + 2, cpres=args.cp_level, multivariate=C > 1, dopt="HOCR", threads=1, **PARAMS)
+        m.set_data(txyz, ttris, S.sxyz, ttris, S.inp, S.ref)
+        m.initialize()
+        cxyz = smooth_warp(cxyz0, seed + 200, 0.1 * mvd)
+        m.reset_cpgrid(cxyz)
+        m.setup()
+        c = m.context()
+        c.set_stream(stream.cuda_stream)
+        models.append(m); ctxs.append(c); subs.append(S)
+        host_bufs.append((torch.from_numpy(S.sxyz.copy()).pin_memory(), torch.from_numpy(cxyz.copy()).pin_memory()))
+    N, L, T = models[0].N, models[0].L, models[0].T
+    lab_host = np.random.default_rng(7).integers(0, L, N).astype(np.int32)
+    lab_dev = torch.from_numpy(lab_host).cuda()
+    d_unary = [torch.empty((L, N), dtype=torch.float32, device="cuda") for _ in range(B)]
+    d_moves = [torch.empty((L, T, 8), dtype=torch.float32, device="cuda") for _ in range(B)]
+    evals_per_subject = N * L + L * T * 8
+    patch_totals = []
+    alg_bytes_unary = []
+    for c in ctxs:
+        off, idx = c.patches()
+        P = np.diff(off).astype(np.int64)
+        alg_bytes_unary.append(int((P * ((48 + 12 * C) * L + (16 + 8 * C)) + 8 * L).sum()))
+        patch_totals.append(int(P.sum()))
+
+    def resident_step():
+        for s in range(B):
+            ctxs[s].unary_table_dev(d_unary[s].data_ptr())
+            ctxs[s].triplet_moves_dev(lab_dev.data_ptr(), -1, d_moves[s].data_ptr())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        resident_step()
+    sync_all()
+    launches0 = sum(c.launch_count() for c in ctxs)
+    for c in ctxs:
+        c.set_timing(2)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        resident_step()
+    e1.record(stream)
+    sync_all()
+    ms_total = e0.elapsed_time(e1)
+    launches = sum(c.launch_count() for c in ctxs) - launches0
+    um, un = 0.0, 0
+    tm_, tn_ = 0.0, 0
+    for c in ctxs:
+        a, b = c.timing_collect("unary_main"); um += a; un += b
+        a, b = c.timing_collect("triplet_moves"); tm_ += a; tn_ += b
+        c.timing_collect("unary"); c.set_timing(0)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = evals_per_subject * B * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host classes, host buffers in/out
+    def e2e_step():
+        for s in range(B):
+            sx, cx = host_bufs[s]
+            models[s].reset_meshspace(sx.numpy())
+            models[s].reset_cpgrid(cx.numpy())
+            models[s].setup()                       # patch construction + unary table -> host double[L][N]
+            models[s].triplet_moves(lab_host, -1)   # -> host double[L][T][8]
+
+    for _ in range(1):
+        e2e_step()
+    sync_all()
+    k_e2e = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / k_e2e
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = evals_per_subject * B * world / float(t.item())
+    Vs = len(txyz)
+    h2d = B * (Vs * 24 + N * 24 + N * 4)
+    d2h = B * (L * N * 4 + L * T * 8 * 8)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        unary_ms = um / max(un, 1)
+        achieved = (np.mean(alg_bytes_unary) / (unary_ms * 1e-3)) / 1e9 if un else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("k_unary_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (unary) / f64 (triplet)",
+            "data": "synthetic",
+            "config": {"workload": workload, "subjects_per_gpu": B, "N": N, "L": L, "T": T, "mean_patch": float(np.mean(patch_totals)) / N,
+                       "evals_per_subject": evals_per_subject, "l2": "working set of B subjects per GPU exceeds the 126 MB L2 (no flush needed)",
+                       "parallelism": f"subjects x{world} (no data-path collective)"},
+            "roofline": {"bound": "hbm", "kernel": "k_unary", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": float(np.mean(alg_bytes_unary)), "avg_launch_ms": unary_ms, "launches_timed": un,
+                         "triplet_moves_avg_ms": tm_ / max(tn_, 1)},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e,
+                    "api": "NonLinearSRegDiscreteModel::reset_meshspace/reset_CPgrid/setupCostFunction + computeTripletMoves"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1:
+            try:
+                threads = os.cpu_count() or 1
+                r = oracle_sample(args.data_level, args.cp_level, C, args.cpu_rows, threads, steps=1, warmup=0)
+                line["cpu_baseline"] = {"value": r["evals_per_s_e2e"], "unit": unit, "cores": threads, "kind": "port",
+                                        "sample": f"{r['rows']} of {r['N']} control points + {r['ntrip']} of {r['T']} triplets x {r['L']} labels x 8 "
+                                                  f"(patches {r['t_patches']:.2f}s 1 thread, unary {r['t_unary']:.2f}s, triplets {r['t_triplet']:.2f}s)",
+                                        "value_tables_only": r["evals_per_s_resident"]}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,16 @@ int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float*
 int msm_pair_table(msm_ctx* ctx, float* out);
 int msm_pair_table_dev(msm_ctx* ctx, float* d_out);
 
+/* Group data term: DiscreteGroupCostFunction::set_patch_data + computePairwiseCost
+ * (src/DiscreteGroupCostFunction.h:39-41, .cpp:32-54).  The std::map<int,double> patches arrive as CSR with ascending
+ * keys: map m = (subject*N_subj + node)*L + label holds (keys[off[m]..off[m+1]), vals[...]).  Pairs come from
+ * msm_set_pairs (global node ids).
+ *  _costs : n queries q[n][3] = (pair, labelA, labelB)
+ *  _moves : the 4 fusion-move costs of include/Fusion/Fusion.h:169-172 for every pair and label alpha, out[P][4]. */
+int msm_set_group_patches(msm_ctx* ctx, long long nmaps, const long long* off, const int* keys, const double* vals);
+int msm_group_pair_costs(msm_ctx* ctx, int n, const int* q, double* out);
+int msm_group_pair_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out);
+
 /* Octree::get_closest_triangle + barycentric weights on the target ([EXT] A3/A4; call sites
  * src/DiscreteCostFunction.cpp:421-433).  tri = index into the `tris` given to msm_set_target; w double[M][3]
  * in that triangle's vertex order. */
@@ -131,8 +141,12 @@ int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]);
 /* Introspection for bench/tests: number of kernels this library launched so far, and per-kernel timing of the
  * last call of the named kernel family measured with CUDA events on the ctx stream (ms, <0 if none). */
 long long msm_launch_count(const msm_ctx* ctx);
-int msm_set_timing(msm_ctx* ctx, int enabled);
+/* mode 0 off; 1 synchronous (msm_last_kernel_ms gives the last duration of a family: "patches", "label_rot", "unary"
+ * (setup + main), "unary_main", "triplet_table", "triplet_moves", "triplet_queries", "pair_table", "group_pair",
+ * "locate"); 2 asynchronous: event pairs are recorded without host syncs and summed by msm_timing_collect. */
+int msm_set_timing(msm_ctx* ctx, int mode);
 double msm_last_kernel_ms(const msm_ctx* ctx, const char* family);
+int msm_timing_collect(msm_ctx* ctx, const char* family, double* total_ms, long long* count);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,8 @@ EXPORTS = [
     "msm_set_pairs", "msm_set_triplets", "msm_set_group", "msm_build_patches", "msm_patch_count", "msm_get_patches",
     "msm_unary_table", "msm_unary_table_dev", "msm_triplet_costs", "msm_triplet_table", "msm_triplet_table_dev", "msm_triplet_moves",
     "msm_triplet_moves_dev", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count",
-    "msm_set_timing", "msm_last_kernel_ms",
+    "msm_set_timing", "msm_last_kernel_ms", "msm_timing_collect", "msm_set_group_patches", "msm_group_pair_costs",
+    "msm_group_pair_moves",
 ]
 
 _lib = None
@@ -78,9 +79,20 @@ class Context:
         self.N = self.L = self.T = self.P = 0
         self.k_begin = self.k_end = 0
 
+    @classmethod
+    def from_handle(cls, handle, N, L, T=0, P=0):
+        """Wrap a context owned by someone else (e.g. a host-side cost function object); close() will not destroy it."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p(handle)
+        self._borrowed = True
+        self.N, self.L, self.T, self.P = N, L, T, P
+        self.k_begin, self.k_end = 0, N
+        return self
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().msm_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                lib().msm_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -235,8 +247,28 @@ class Context:
     def launch_count(self):
         return int(lib().msm_launch_count(self._h))
 
-    def set_timing(self, on=True):
-        self._ck(lib().msm_set_timing(self._h, int(on)))
+    def set_group_patches(self, off, keys, vals):
+        off = np.ascontiguousarray(off, np.int64); keys, pk = _i(keys); vals, pv = _d(vals)
+        self._ck(lib().msm_set_group_patches(self._h, C.c_longlong(len(off) - 1), off.ctypes.data_as(C.POINTER(C.c_longlong)), pk, pv))
+
+    def group_pair_costs(self, q):
+        q, pq = _i(q); out = np.empty(len(q), np.float64)
+        self._ck(lib().msm_group_pair_costs(self._h, len(q), pq, out.ctypes.data_as(c_dp)))
+        return out
+
+    def group_pair_moves(self, labeling, alpha):
+        labeling, pl = _i(labeling); out = np.empty((self.P, 4), np.float64)
+        self._ck(lib().msm_group_pair_moves(self._h, pl, int(alpha), out.ctypes.data_as(c_dp)))
+        return out
+
+    def set_timing(self, mode=1):
+        """0 off, 1 synchronous per-family timing, 2 asynchronous (timing_collect)."""
+        self._ck(lib().msm_set_timing(self._h, int(mode)))
+
+    def timing_collect(self, family):
+        tot = C.c_double(); cnt = C.c_longlong()
+        self._ck(lib().msm_timing_collect(self._h, family.encode(), C.byref(tot), C.byref(cnt)))
+        return tot.value, cnt.value
 
     def last_kernel_ms(self, family):
         return float(lib().msm_last_kernel_ms(self._h, family.encode()))

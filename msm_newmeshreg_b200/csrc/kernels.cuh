@@ -157,6 +157,108 @@ __global__ void __launch_bounds__(256) k_patch(PatchArgs a) {
     }
 }
 
+// ---- binned variant: source vertices are counting-sorted into a uniform voxel grid whose cell size is the largest patch
+// chord, so a control point only tests the vertices of the <= 27 cells around it instead of the whole mesh (the
+// reference's O(N*V) scan, src/DiscreteCostFunction.cpp:398-400).  Membership decisions are the same fp64 tests as above;
+// each patch list is sorted ascending afterwards (the reference's order), which also makes the result deterministic.
+struct BinGrid {
+    int G;            // cells per dimension
+    double lo, inv_h; // cell = floor((x - lo) * inv_h), clamped
+    int* cell_start;  // [G^3 + 1] (exclusive scan of counts)
+    int* cell_fill;   // [G^3]
+    int* sorted;      // [V] vertex ids grouped by cell
+};
+__device__ __forceinline__ int bin_coord(const BinGrid& g, double x) {
+    int c = (int)floor((x - g.lo) * g.inv_h);
+    return min(g.G - 1, max(0, c));
+}
+__global__ void __launch_bounds__(256) k_bin_count(BinGrid g, int V, const double* __restrict__ src, int* __restrict__ cell_of, int* __restrict__ counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = (bin_coord(g, src[3 * i]) * g.G + bin_coord(g, src[3 * i + 1])) * g.G + bin_coord(g, src[3 * i + 2]);
+    cell_of[i] = c;
+    atomicAdd(counts + c, 1);
+}
+__global__ void __launch_bounds__(256) k_bin_fill(BinGrid g, int V, const int* __restrict__ cell_of) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    const int c = cell_of[i];
+    g.sorted[g.cell_start[c] + atomicAdd(g.cell_fill + c, 1)] = i;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_patch_binned(PatchArgs a, BinGrid g, int cap /*smem ints, FILL only*/) {
+    extern __shared__ int s_list[];
+    __shared__ int s_n;
+    const int row = blockIdx.x, k = a.k_begin + row, tid = threadIdx.x;
+    const double cx = a.cp[3 * k], cy = a.cp[3 * k + 1], cz = a.cp[3 * k + 2];
+    const float cxf = (float)cx, cyf = (float)cy, czf = (float)cz;
+    double c2lo, c2hi; float c2f;
+    patch_thresholds(a.range * a.maxsep[k], c2lo, c2hi, c2f);
+    c2f += 1e-2f;
+    const double reach = sqrt(c2hi) * (1.0 + 1e-9);
+    int acc0 = 0, acc1 = 0;
+    if (FILL && a.acc_off) { acc0 = a.acc_off[row]; acc1 = a.acc_off[row + 1]; }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int x0 = bin_coord(g, cx - reach), x1 = bin_coord(g, cx + reach);
+    const int y0 = bin_coord(g, cy - reach), y1 = bin_coord(g, cy + reach);
+    const int z0 = bin_coord(g, cz - reach), z1 = bin_coord(g, cz + reach);
+    int mine = 0;
+    for (int x = x0; x <= x1; x++)
+        for (int y = y0; y <= y1; y++) {
+            // cells (x,y,z0..z1) are contiguous in memory: one candidate range per (x,y)
+            const int c0 = (x * g.G + y) * g.G + z0, c1 = (x * g.G + y) * g.G + z1;
+            const int b = g.cell_start[c0], e = g.cell_start[c1 + 1];
+            for (int s = b + tid; s < e; s += 128) {
+                const int i = g.sorted[s];
+                const int cls = patch_classify(a, i, cx, cy, cz, cxf, cyf, czf, c2lo, c2hi, c2f);
+                bool in = (cls == 1);
+                if (cls == 2) {
+                    if (!FILL) {
+                        int slot = atomicAdd(a.unc_count, 1);
+                        if (slot < a.unc_cap) a.unc[slot] = make_int2(k, i);
+                    } else {
+                        for (int q = acc0; q < acc1; q++)
+                            if (a.acc_idx[q] == i) { in = true; break; }
+                    }
+                }
+                if (in) {
+                    if (!FILL) mine++;
+                    else { const int p = atomicAdd(&s_n, 1); if (p < cap) s_list[p] = i; }
+                }
+            }
+        }
+    if (!FILL) {
+        mine = (int)warp_sum((float)mine);
+        if ((tid & 31) == 0) atomicAdd(&s_n, mine);
+        __syncthreads();
+        if (tid == 0) a.counts[row] = s_n;
+    } else {
+        __syncthreads();
+        const int n = min(s_n, cap);
+        // bitonic sort of s_list[0..n) padded with INT_MAX to the next power of two
+        int m = 1;
+        while (m < n) m <<= 1;
+        for (int i = n + tid; i < m; i += 128) s_list[i] = 0x7fffffff;
+        __syncthreads();
+        for (int sz = 2; sz <= m; sz <<= 1)
+            for (int st = sz >> 1; st > 0; st >>= 1) {
+                for (int i = tid; i < m; i += 128) {
+                    const int j = i ^ st;
+                    if (j > i) {
+                        const int vi = s_list[i], vj = s_list[j];
+                        const bool up = (i & sz) == 0;
+                        if ((vi > vj) == up) { s_list[i] = vj; s_list[j] = vi; }
+                    }
+                }
+                __syncthreads();
+            }
+        const int o = a.off[row];
+        for (int i = tid; i < n; i += 128) a.idx[o + i] = s_list[i];
+    }
+}
+
 // exclusive scan of (counts + accepted) over the shard rows; also total and max.  Single CTA.
 __global__ void __launch_bounds__(1024) k_patch_scan(int n, const int* __restrict__ counts, const int* __restrict__ acc_off,
                                                      int* __restrict__ off, int* __restrict__ total_max) {
@@ -478,6 +580,64 @@ __global__ void __launch_bounds__(128) k_pair_queries(PairArgs a, int n, const i
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = pair_cost(a, q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+}
+
+// =========================================================================================================
+// Group data term — DiscreteGroupCostFunction::computePairwiseCost (src/DiscreteGroupCostFunction.cpp:32-54):
+// Pearson correlation over the intersection of two (template vertex -> value) patch maps, in A's key order, unweighted,
+// returned as 1-(1+rho)/2 (no lambda).  Maps are CSR with ascending keys (std::map order), so the intersection is a
+// merge join.  One thread per query; fp64; two passes like the reference (means, then centred sums).
+// =========================================================================================================
+struct GroupPairArgs {
+    int L, N_subj;
+    const int* pairs;            // [P][2] global node ids
+    const long long* moff;       // [nmaps+1]
+    const int* mkey;             // ascending within a map
+    const double* mval;
+};
+
+__device__ __forceinline__ double group_pair_cost(const GroupPairArgs& a, int pr, int la, int lb) {
+    const int ga = a.pairs[2 * pr], gb = a.pairs[2 * pr + 1];
+    // patch_data index = subject*N*L + node*L + label = global_node*L + label
+    const long long a0 = a.moff[(long long)ga * a.L + la], a1 = a.moff[(long long)ga * a.L + la + 1];
+    const long long b0 = a.moff[(long long)gb * a.L + lb], b1 = a.moff[(long long)gb * a.L + lb + 1];
+    double sA = 0, sB = 0; int n = 0;
+    for (long long i = a0, j = b0; i < a1 && j < b1;) {
+        const int ka = a.mkey[i], kb = a.mkey[j];
+        if (ka == kb) { sA += a.mval[i]; sB += a.mval[j]; n++; i++; j++; }
+        else if (ka < kb) i++;
+        else j++;
+    }
+    if (n > 0) { sA /= n; sB /= n; }           // src/similarities.cc:139-142 (sum of unit weights = n)
+    double pr_ = 0, vA = 0, vB = 0;
+    for (long long i = a0, j = b0; i < a1 && j < b1;) {
+        const int ka = a.mkey[i], kb = a.mkey[j];
+        if (ka == kb) {
+            const double da = a.mval[i] - sA, db = a.mval[j] - sB;
+            pr_ += da * db; vA += da * da; vB += db * db; i++; j++;
+        } else if (ka < kb) i++;
+        else j++;
+    }
+    if (n > 0) { pr_ /= n; vA /= n; vB /= n; }
+    const double rho = (vA == 0.0 || vB == 0.0) ? 0.0 : pr_ / (sqrt(vA) * sqrt(vB));
+    return 1.0 - (1.0 + rho) / 2.0;
+}
+
+__global__ void __launch_bounds__(128) k_group_pair_queries(GroupPairArgs a, int n, const int* __restrict__ q, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = group_pair_cost(a, q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+}
+
+// fusion-move costs of include/Fusion/Fusion.h:169-172: (cur,cur) (cur,alpha) (alpha,cur) (alpha,alpha) per pair
+__global__ void __launch_bounds__(128) k_group_pair_moves(GroupPairArgs a, int P, const int* __restrict__ labeling, int alpha,
+                                                          double* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P * 4) return;
+    const int pr = (int)(gid >> 2), c = (int)(gid & 3);
+    const int la = (c & 2) ? alpha : labeling[a.pairs[2 * pr]];
+    const int lb = (c & 1) ? alpha : labeling[a.pairs[2 * pr + 1]];
+    out[gid] = group_pair_cost(a, pr, la, lb);
 }
 
 // =========================================================================================================

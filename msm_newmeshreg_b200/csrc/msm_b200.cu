@@ -59,8 +59,11 @@ struct msm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     long long launches = 0;
-    bool timing = false;
+    int timing_mode = 0;  // 0 off, 1 synchronous, 2 asynchronous (collected later)
     std::map<std::string, float> last_ms;
+    struct PendingEv { const char* name; cudaEvent_t e0, e1; };
+    std::vector<PendingEv> ev_pending;
+    std::vector<cudaEvent_t> ev_free;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     msm_params par;
@@ -97,6 +100,8 @@ struct msm_ctx {
     int P = 0, Tn = 0;
     DevBuf d_pairs, d_trip;
     int S = 1, N_subj = 0, T_subj = 0;
+    long long n_maps = 0;            // group patch maps (set_patch_data)
+    DevBuf d_moff, d_mkey, d_mval;
 
     // patches
     bool have_patches = false;
@@ -104,6 +109,7 @@ struct msm_ctx {
     int maxP = 0;
     DevBuf d_counts, d_off, d_idx, d_unc, d_unc_count, d_acc_off, d_acc_idx, d_totmax;
     DevBuf d_px, d_py, d_pz, d_pa, d_pw;
+    DevBuf d_cell_counts, d_cell_start, d_cell_fill, d_cell_of, d_sorted;  // voxel grid of the source vertices
     DevBuf d_pcx, d_pcy, d_pcz, d_hint_face, d_lab12, d_tref;  // k_unary_setup outputs
     int pack_cp = 0;
 
@@ -135,16 +141,32 @@ struct msm_ctx {
 
 namespace {
 
+// Per-kernel-family timing with CUDA events on the launching stream.  mode 1: synchronous (event pair, sync, store the
+// last duration).  mode 2: asynchronous — event pairs are only recorded; msm_timing_collect() reads them after the
+// caller's own synchronisation, so a timed region is not perturbed by host syncs.
 struct Timer {
     msm_ctx* ctx; const char* name;
-    Timer(msm_ctx* c, const char* n) : ctx(c), name(n) { if (ctx->timing) cudaEventRecord(ctx->ev0, ctx->stream); }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    Timer(msm_ctx* c, const char* n) : ctx(c), name(n) {
+        if (ctx->timing_mode != 0) {
+            if (ctx->ev_free.size() < 2) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ctx->ev_free.push_back(a); ctx->ev_free.push_back(b); }
+            e0 = ctx->ev_free.back(); ctx->ev_free.pop_back();
+            e1 = ctx->ev_free.back(); ctx->ev_free.pop_back();
+            cudaEventRecord(e0, ctx->stream);
+        }
+    }
     ~Timer() {
-        if (ctx->timing) {
-            cudaEventRecord(ctx->ev1, ctx->stream);
-            cudaEventSynchronize(ctx->ev1);
+        if (!e0) return;
+        if (ctx->timing_mode == 1) {
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
             float ms = -1.f;
-            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            cudaEventElapsedTime(&ms, e0, e1);
             ctx->last_ms[name] = ms;
+            ctx->ev_free.push_back(e0); ctx->ev_free.push_back(e1);
+        } else {
+            cudaEventRecord(e1, ctx->stream);
+            ctx->ev_pending.push_back({name, e0, e1});
         }
     }
 };
@@ -583,7 +605,41 @@ int msm_build_patches(msm_ctx* ctx) {
     a.unc = ctx->d_unc.as<int2>(); a.unc_cap = unc_cap; a.unc_count = ctx->d_unc_count.as<int>();
     a.acc_off = nullptr; a.acc_idx = nullptr; a.off = nullptr; a.idx = nullptr;
     Timer tm(ctx, "patches");
-    k_patch<false><<<Ns, 256, 0, ctx->stream>>>(a);
+    // voxel grid over the source vertices (cell >= largest patch chord); brute force only for degenerate sizes
+    BinGrid bg{};
+    bool binned = false;
+    {
+        double maxsep = 0.0, Rb = 0.0;
+        for (int k = ctx->k_begin; k < ctx->k_end; k++) maxsep = std::max(maxsep, ctx->h_maxsep[k]);
+        for (double v : ctx->h_src) Rb = std::max(Rb, std::fabs(v));
+        Rb = Rb * (1.0 + 1e-9) + 1e-6;
+        const double half = ctx->par.range * maxsep / 200.0;
+        const char* brute = getenv("MSM_PATCH_BRUTE");
+        if (half < 1.5 && !(brute && atoi(brute))) {
+            const double chord = 200.0 * std::sin(half) * (1.0 + 1e-6);
+            const int G = (int)std::min(64.0, std::floor(2.0 * Rb / std::max(chord, 1e-9)));
+            if (G >= 3) {
+                const size_t nc = (size_t)G * G * G;
+                CK(ctx->d_cell_counts.ensure(nc * 4)); CK(ctx->d_cell_start.ensure((nc + 1) * 4)); CK(ctx->d_cell_fill.ensure(nc * 4));
+                CK(ctx->d_cell_of.ensure((size_t)ctx->Vs * 4)); CK(ctx->d_sorted.ensure((size_t)ctx->Vs * 4));
+                CK(cudaMemsetAsync(ctx->d_cell_counts.p, 0, nc * 4, ctx->stream));
+                CK(cudaMemsetAsync(ctx->d_cell_fill.p, 0, nc * 4, ctx->stream));
+                bg.G = G; bg.lo = -Rb; bg.inv_h = G / (2.0 * Rb);
+                bg.cell_start = ctx->d_cell_start.as<int>(); bg.cell_fill = ctx->d_cell_fill.as<int>(); bg.sorted = ctx->d_sorted.as<int>();
+                k_bin_count<<<(ctx->Vs + 255) / 256, 256, 0, ctx->stream>>>(bg, ctx->Vs, ctx->d_src.as<double>(), ctx->d_cell_of.as<int>(),
+                                                                           ctx->d_cell_counts.as<int>());
+                KLAUNCH_CHECK();
+                k_patch_scan<<<1, 1024, 0, ctx->stream>>>((int)nc, ctx->d_cell_counts.as<int>(), nullptr, ctx->d_cell_start.as<int>(),
+                                                          ctx->d_totmax.as<int>());
+                KLAUNCH_CHECK();
+                k_bin_fill<<<(ctx->Vs + 255) / 256, 256, 0, ctx->stream>>>(bg, ctx->Vs, ctx->d_cell_of.as<int>());
+                KLAUNCH_CHECK();
+                binned = true;
+            }
+        }
+    }
+    if (binned) k_patch_binned<false><<<Ns, 128, 0, ctx->stream>>>(a, bg, 0);
+    else k_patch<false><<<Ns, 256, 0, ctx->stream>>>(a);
     KLAUNCH_CHECK();
     int n_unc = 0;
     CK(cudaMemcpyAsync(&n_unc, ctx->d_unc_count.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -626,7 +682,14 @@ int msm_build_patches(msm_ctx* ctx) {
     a.acc_off = have_acc ? ctx->d_acc_off.as<int>() : nullptr;
     a.acc_idx = have_acc ? ctx->d_acc_idx.as<int>() : nullptr;
     a.off = ctx->d_off.as<int>(); a.idx = ctx->d_idx.as<int>();
-    k_patch<true><<<Ns, 256, 0, ctx->stream>>>(a);
+    int cap = 1;
+    while (cap < ctx->maxP) cap <<= 1;
+    if (binned && cap <= 16384) {
+        if (cap * 4 > 48 * 1024) CK(cudaFuncSetAttribute(k_patch_binned<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 4));
+        k_patch_binned<true><<<Ns, 128, (size_t)cap * 4, ctx->stream>>>(a, bg, cap);
+    } else {
+        k_patch<true><<<Ns, 256, 0, ctx->stream>>>(a);
+    }
     KLAUNCH_CHECK();
     // packed sample streams
     const int Cp = ctx->multivariate ? 4 * ((ctx->Cs + 3) / 4) : 1;
@@ -732,13 +795,16 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_unary<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_unary<Q><<<grid, 256, smem, ctx->stream>>>(a);                                                            \
     } while (0)
-    switch (CQ) {
-        case 0: LAUNCH_UNARY(0); break;
-        case 1: LAUNCH_UNARY(1); break;
-        case 2: LAUNCH_UNARY(2); break;
-        case 3: LAUNCH_UNARY(3); break;
-        case 4: LAUNCH_UNARY(4); break;
-        default: FAIL("unsupported channel count");
+    {
+        Timer tmain(ctx, "unary_main");
+        switch (CQ) {
+            case 0: LAUNCH_UNARY(0); break;
+            case 1: LAUNCH_UNARY(1); break;
+            case 2: LAUNCH_UNARY(2); break;
+            case 3: LAUNCH_UNARY(3); break;
+            case 4: LAUNCH_UNARY(4); break;
+            default: FAIL("unsupported channel count");
+        }
     }
 #undef LAUNCH_UNARY
     KLAUNCH_CHECK();
@@ -875,6 +941,73 @@ int msm_pair_table(msm_ctx* ctx, float* out) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+int msm_set_group_patches(msm_ctx* ctx, long long nmaps, const long long* off, const int* keys, const double* vals) {
+    CK(cudaSetDevice(ctx->device));
+    if (nmaps != (long long)ctx->N * ctx->L) FAIL("msm_set_group_patches: need one map per (global node, label)");
+    for (long long m = 0; m < nmaps; m++)
+        for (long long e = off[m] + 1; e < off[m + 1]; e++)
+            if (keys[e - 1] >= keys[e]) FAIL("msm_set_group_patches: keys must be strictly ascending within a map");
+    ctx->n_maps = nmaps;
+    if (upload(ctx, ctx->d_moff, off, (size_t)nmaps + 1)) return 1;
+    if (upload(ctx, ctx->d_mkey, keys, (size_t)off[nmaps])) return 1;
+    if (upload(ctx, ctx->d_mval, vals, (size_t)off[nmaps])) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static int group_pair_args(msm_ctx* ctx, GroupPairArgs& a) {
+    if (ctx->P <= 0) FAIL("set_pairs must be called first");
+    if (ctx->n_maps != (long long)ctx->N * ctx->L) FAIL("set_patch_data (msm_set_group_patches) must be called first");
+    a.L = ctx->L; a.N_subj = ctx->N_subj;
+    a.pairs = ctx->d_pairs.as<int>();
+    a.moff = ctx->d_moff.as<long long>(); a.mkey = ctx->d_mkey.as<int>(); a.mval = ctx->d_mval.as<double>();
+    return 0;
+}
+
+int msm_group_pair_costs(msm_ctx* ctx, int n, const int* q, double* out) {
+    CK(cudaSetDevice(ctx->device));
+    GroupPairArgs a;
+    if (group_pair_args(ctx, a)) return 1;
+    if (n <= 0) return 0;
+    for (int i = 0; i < n; i++)
+        if (q[3 * i] < 0 || q[3 * i] >= ctx->P || q[3 * i + 1] < 0 || q[3 * i + 1] >= ctx->L || q[3 * i + 2] < 0 || q[3 * i + 2] >= ctx->L)
+            FAIL("msm_group_pair_costs: query out of range");
+    CK(ctx->d_scratch.ensure((size_t)n * 12));
+    CK(ctx->d_scratch2.ensure((size_t)n * 8));
+    CK(cudaMemcpyAsync(ctx->d_scratch.p, q, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timer tm(ctx, "group_pair");
+        k_group_pair_queries<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a, n, ctx->d_scratch.as<int>(), ctx->d_scratch2.as<double>());
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_group_pair_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out) {
+    CK(cudaSetDevice(ctx->device));
+    GroupPairArgs a;
+    if (group_pair_args(ctx, a)) return 1;
+    if (alpha < 0 || alpha >= ctx->L) FAIL("msm_group_pair_moves: label out of range");
+    for (int i = 0; i < ctx->N; i++)
+        if (labeling[i] < 0 || labeling[i] >= ctx->L) FAIL("msm_group_pair_moves: labeling out of range");
+    CK(ctx->d_scratch.ensure((size_t)ctx->N * 4));
+    CK(ctx->d_scratch2.ensure((size_t)ctx->P * 4 * 8));
+    CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timer tm(ctx, "group_pair");
+        const long long n = (long long)ctx->P * 4;
+        k_group_pair_moves<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, ctx->P, ctx->d_scratch.as<int>(), alpha,
+                                                                             ctx->d_scratch2.as<double>());
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)ctx->P * 4 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 int msm_locate(msm_ctx* ctx, const double* pts, int M, int* tri, double* w) {
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_target) FAIL("msm_set_target must be called first");
@@ -934,7 +1067,22 @@ int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]) {
 }
 
 long long msm_launch_count(const msm_ctx* ctx) { return ctx->launches; }
-int msm_set_timing(msm_ctx* ctx, int enabled) { ctx->timing = enabled != 0; return 0; }
+int msm_set_timing(msm_ctx* ctx, int mode) { ctx->timing_mode = mode; return 0; }
+int msm_timing_collect(msm_ctx* ctx, const char* family, double* total_ms, long long* count) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *total_ms = 0.0; *count = 0;
+    std::vector<msm_ctx::PendingEv> keep;
+    for (auto& p : ctx->ev_pending) {
+        if (std::strcmp(p.name, family) == 0) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { *total_ms += ms; (*count)++; }
+            ctx->ev_free.push_back(p.e0); ctx->ev_free.push_back(p.e1);
+        } else keep.push_back(p);
+    }
+    ctx->ev_pending.swap(keep);
+    return 0;
+}
 double msm_last_kernel_ms(const msm_ctx* ctx, const char* family) {
     auto it = ctx->last_ms.find(family);
     return it == ctx->last_ms.end() ? -1.0 : (double)it->second;

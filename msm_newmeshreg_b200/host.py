@@ -1,0 +1,162 @@
+"""ctypes binding of libmsm_host.so — the host-side C++ mirror of the reference's DiscreteModel / DiscreteCostFunction
+classes (msm_newmeshreg_b200/host/src), driven through the flat entry points of host/harness.cpp.
+
+`Model` follows the reference driver's call sequence (src/mesh_registration.cpp:316-397): set_data -> initialize ->
+[reset_meshspace -> setup -> unary / per-element costs -> (optimiser) -> apply_labeling]*.
+Every cost is evaluated on the GPU (no CPU fallback); geometry helpers (icosphere, label grid, cliques) are host code.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libmsm_host.so")
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+_lib = None
+
+
+def bind(lib):
+    lib.msmhost_last_error.restype = C.c_char_p
+    lib.msmhost_model_create.restype = C.c_void_p
+    lib.msmhost_model_create.argtypes = [C.c_double] * 6 + [C.c_int] * 6 + [C.c_double, C.c_int, C.c_char_p, C.c_int]
+    lib.msmhost_model_total.restype = C.c_double
+    for f in ("msmhost_model_destroy", "msmhost_model_set_data", "msmhost_model_initialize", "msmhost_model_sizes",
+              "msmhost_model_reset_meshspace", "msmhost_model_reset_cpgrid", "msmhost_model_setup", "msmhost_model_unary",
+              "msmhost_model_get", "msmhost_model_costs", "msmhost_model_set_labeling", "msmhost_model_get_labeling",
+              "msmhost_model_total", "msmhost_model_apply_labeling", "msmhost_model_triplet_moves"):
+        getattr(lib, f).argtypes = None
+    return lib
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise RuntimeError(f"{HOST_LIB_PATH} is missing: run __graft_entry__.build()")
+        from . import _capi
+        _capi.lib()  # libmsm_b200.so first (dependency)
+        _lib = bind(C.CDLL(HOST_LIB_PATH))
+    return _lib
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(c_dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(c_ip)
+
+
+def icosphere(level, radius=100.0, _lib_override=None):
+    L = _lib_override or lib()
+    nv, nf = C.c_int(), C.c_int()
+    L.msmhost_icosphere_counts(level, C.byref(nv), C.byref(nf))
+    xyz = np.empty((nv.value, 3)); tris = np.empty((nf.value, 3), np.int32)
+    L.msmhost_icosphere(level, C.c_double(radius), xyz.ctypes.data_as(c_dp), tris.ctypes.data_as(c_ip))
+    return xyz, tris
+
+
+class Model:
+    """NonLinearSRegDiscreteModel (+ its GPU-backed cost function) behind the harness."""
+
+    def __init__(self, lam=0.1, rexp=2.0, mu=0.4, kappa=1.6, k_exp=2.0, rng=1.0, simmeasure=2, rmode=3, dweight=False, anorm=False,
+                 sgres=4, cpres=2, labeldist=0.5, multivariate=False, dopt="HOCR", threads=1, _lib_override=None):
+        self._L = _lib_override or lib()
+        self.h = self._L.msmhost_model_create(lam, rexp, mu, kappa, k_exp, rng, simmeasure, rmode, int(dweight), int(anorm), sgres, cpres,
+                                              labeldist, int(multivariate), dopt.encode(), threads)
+        if not self.h:
+            raise HostError(self._L.msmhost_last_error().decode())
+        self.h = C.c_void_p(self.h)
+        self.cpres = cpres
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.msmhost_model_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise HostError(self._L.msmhost_last_error().decode())
+
+    def set_data(self, txyz, ttris, sxyz, stris, inp, ref):
+        txyz, p1 = _d(txyz); ttris, p2 = _i(ttris); sxyz, p3 = _d(sxyz); stris, p4 = _i(stris)
+        inp = np.atleast_2d(inp); ref = np.atleast_2d(ref); inp, p5 = _d(inp); ref, p6 = _d(ref)
+        self.Vs = len(sxyz)
+        self._ck(self._L.msmhost_model_set_data(self.h, p1, len(txyz), p2, len(ttris), p3, len(sxyz), p4, len(stris), p5, p6, inp.shape[0]))
+
+    def initialize(self):
+        self._ck(self._L.msmhost_model_initialize(self.h, self.cpres))
+        self._sizes()
+
+    def _sizes(self):
+        n, l, p, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._L.msmhost_model_sizes(self.h, C.byref(n), C.byref(l), C.byref(p), C.byref(t))
+        self.N, self.L, self.P, self.T = n.value, l.value, p.value, t.value
+
+    def reset_meshspace(self, sxyz):
+        sxyz, p = _d(sxyz); self._ck(self._L.msmhost_model_reset_meshspace(self.h, p))
+
+    def reset_cpgrid(self, cxyz):
+        cxyz, p = _d(cxyz); self._ck(self._L.msmhost_model_reset_cpgrid(self.h, p))
+
+    def setup(self):
+        self._ck(self._L.msmhost_model_setup(self.h)); self._sizes()
+
+    def unary(self):
+        out = np.empty((self.L, self.N))
+        self._ck(self._L.msmhost_model_unary(self.h, out.ctypes.data_as(c_dp)))
+        return out
+
+    def cpgrid(self):
+        out = np.empty((self.N, 3)); self._ck(self._L.msmhost_model_get(self.h, out.ctypes.data_as(c_dp), None, None, None)); return out
+
+    def labels(self):
+        out = np.empty((self.L, 3)); self._ck(self._L.msmhost_model_get(self.h, None, out.ctypes.data_as(c_dp), None, None)); return out
+
+    def pairs(self):
+        out = np.empty((self.P, 2), np.int32); self._ck(self._L.msmhost_model_get(self.h, None, None, out.ctypes.data_as(c_ip), None)); return out
+
+    def triplets(self):
+        out = np.empty((self.T, 3), np.int32); self._ck(self._L.msmhost_model_get(self.h, None, None, None, out.ctypes.data_as(c_ip))); return out
+
+    def costs(self, kind, q):
+        q, pq = _i(q); out = np.empty(len(q))
+        self._ck(self._L.msmhost_model_costs(self.h, {"unary": 0, "pair": 1, "triplet": 2}[kind], len(q), pq, out.ctypes.data_as(c_dp)))
+        return out
+
+    def set_labeling(self, lab):
+        lab, p = _i(lab); self._L.msmhost_model_set_labeling(self.h, p)
+
+    def labeling(self):
+        out = np.empty(self.N, np.int32); self._L.msmhost_model_get_labeling(self.h, out.ctypes.data_as(c_ip)); return out
+
+    def total(self):
+        return float(self._L.msmhost_model_total(self.h))
+
+    def apply_labeling(self):
+        out = np.empty((self.N, 3)); self._ck(self._L.msmhost_model_apply_labeling(self.h, out.ctypes.data_as(c_dp))); return out
+
+    def context(self):
+        """The cost function's device context as a (borrowed) msm_newmeshreg_b200.Context."""
+        from ._capi import Context
+        self._L.msmhost_model_context.restype = C.c_void_p
+        return Context.from_handle(self._L.msmhost_model_context(self.h), self.N, self.L, self.T, self.P)
+
+    def triplet_moves(self, labeling, alpha):
+        labeling, p = _i(labeling)
+        out = np.empty((self.L, self.T, 8) if alpha < 0 else (self.T, 8))
+        self._ck(self._L.msmhost_model_triplet_moves(self.h, p, int(alpha), out.ctypes.data_as(c_dp)))
+        return out

@@ -1,0 +1,254 @@
+// harness.cpp — flat C entry points over the host-side mirror classes (src/DiscreteModel.h, src/DiscreteCostFunction.h)
+// so that Python (tests, bench.py) can drive the SAME call sequence the reference's driver makes
+// (src/mesh_registration.cpp:316-397: reset_meshspace -> setupCostFunction -> computeUnaryCosts -> optimise ->
+// applyLabeling).  Compiled twice:
+//   * libmsm_host.so  (product): model + GPU-backed cost functions only;
+//   * oracle/_ref/libref_optim.so (test infrastructure, -DWITH_REF_OPTIM): additionally the UNMODIFIED vendored optimisers
+//     from /root/reference/include (FastPD, ELC/HOCR, Fusion), compiled where they lie against these FSL-free headers.
+#include <cstring>
+#include <memory>
+
+#include "src/DiscreteGroupModel.h"
+#include "src/DiscreteModel.h"
+
+#ifdef WITH_REF_OPTIM
+#define HAS_FPD
+#define HAS_HOCR
+#include "FastPD/FastPD.h"
+#include "Fusion/Fusion.h"
+#endif
+
+using namespace newmeshreg;
+
+namespace {
+thread_local std::string g_err;
+struct ModelBox {
+    std::shared_ptr<NonLinearSRegDiscreteModel> model;
+    std::shared_ptr<DiscreteGroupModel> group;
+    myparam params;
+    newresampler::Mesh target, source;
+};
+newresampler::Mesh mesh_from(const double* xyz, int nv, const int* tris, int nf) {
+    newresampler::Mesh m;
+    m.set(xyz, nv, tris, nf);
+    return m;
+}
+template <typename F>
+int guard(F&& f) {
+    try { f(); return 0; }
+    catch (const MeshregException& e) { g_err = e.errmesg ? e.errmesg : "MeshregException"; return 1; }
+    catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// A model whose costs are explicit tables: lets the optimisers run from oracle- or GPU-produced tables alike.
+class TableCostFunction : public DiscreteCostFunction {
+public:
+    TableCostFunction(int N, int L, int P, int T, const double* unary, const double* pairtab, const double* triptab)
+        : U(unary, unary + (size_t)N * L), PT(pairtab ? pairtab : nullptr, pairtab ? pairtab + (size_t)P * L * L : nullptr),
+          TT(triptab ? triptab : nullptr, triptab ? triptab + (size_t)T * L * L * L : nullptr) {
+        initialize(N, L, P, T);
+        std::copy(U.begin(), U.end(), unarycosts);
+    }
+    void computeUnaryCosts() override { std::copy(U.begin(), U.end(), unarycosts); }
+    double computeUnaryCost(int node, int label) override { return U[(size_t)label * m_num_nodes + node]; }
+    double computePairwiseCost(int pair, int la, int lb) override { return PT.empty() ? 0.0 : PT[((size_t)pair * m_num_labels + lb) * m_num_labels + la]; }
+    double computeTripletCost(int t, int a, int b, int c) override {
+        const size_t L = m_num_labels;
+        return TT.empty() ? 0.0 : TT[(((size_t)t * L + a) * L + b) * L + c];
+    }
+private:
+    std::vector<double> U, PT, TT;
+};
+class TableModel : public DiscreteModel {
+public:
+    TableModel(int N, int L, int P, const int* prs, int T, const int* trs, std::shared_ptr<TableCostFunction> cf) : costfct(cf) {
+        m_num_nodes = N; m_num_labels = L; m_num_pairs = P; m_num_triplets = T;
+        initLabeling();
+        pairs = new int[2 * (size_t)std::max(P, 1)];
+        triplets = new int[3 * (size_t)std::max(T, 1)];
+        if (P) std::copy(prs, prs + 2 * (size_t)P, pairs);
+        if (T) std::copy(trs, trs + 3 * (size_t)T, triplets);
+    }
+    std::shared_ptr<DiscreteCostFunction> getCostFunction() override { return costfct; }
+    void computeUnaryCosts() override { costfct->computeUnaryCosts(); }
+    double computeUnaryCost(int n, int l) override { return costfct->computeUnaryCost(n, l); }
+    double computePairwiseCost(int p, int a, int b) override { return costfct->computePairwiseCost(p, a, b); }
+    double computeTripletCost(int t, int a, int b, int c) override { return costfct->computeTripletCost(t, a, b, c); }
+    double evaluateTotalCostSum() override { return costfct->evaluateTotalCostSum(labeling, pairs, triplets); }
+private:
+    std::shared_ptr<TableCostFunction> costfct;
+};
+}  // namespace
+
+extern "C" {
+
+const char* msmhost_last_error() { return g_err.c_str(); }
+
+// newresampler::make_mesh_from_icosa + true_rescale (src/mesh_registration.cpp:67-69)
+void msmhost_icosphere_counts(int level, int* nv, int* nf) {
+    long f = 20; for (int i = 0; i < level; i++) f *= 4;
+    *nf = (int)f; *nv = (int)(f / 2 + 2);
+}
+void msmhost_icosphere(int level, double radius, double* xyz, int* tris) {
+    newresampler::Mesh m = newresampler::make_mesh_from_icosa(level);
+    newresampler::true_rescale(m, radius);
+    auto c = m.coords(); auto f = m.faces();
+    std::memcpy(xyz, c.data(), c.size() * sizeof(double));
+    std::memcpy(tris, f.data(), f.size() * sizeof(int));
+}
+
+// ---- NonLinearSRegDiscreteModel ----------------------------------------------------------------------------------
+void* msmhost_model_create(double lambda, double rexp, double mu, double kappa, double kexp, double range, int simmeasure, int rmode,
+                           int dweight, int anorm, int sgres, int cpres, double labeldist, int multivariate, const char* dopt, int threads) {
+    auto* b = new ModelBox();
+    b->params = default_parameters();
+    myparam& P = b->params;
+    P["lambda"] = (float)lambda; P["exponent"] = (float)rexp; P["shearmodulus"] = (float)mu; P["bulkmodulus"] = (float)kappa;
+    P["kexponent"] = (float)kexp; P["range"] = (float)range; P["simmeasure"] = simmeasure; P["regularisermode"] = rmode;
+    P["weight"] = dweight != 0; P["anorm"] = anorm != 0; P["SGres"] = sgres; P["CPres"] = cpres; P["labeldist"] = (float)labeldist;
+    P["multivariate"] = multivariate != 0; P["dOPT"] = std::string(dopt); P["numthreads"] = threads;
+    if (guard([&] { b->model = std::make_shared<NonLinearSRegDiscreteModel>(P); })) { delete b; return nullptr; }
+    return b;
+}
+void msmhost_model_destroy(void* h) { delete (ModelBox*)h; }
+
+int msmhost_model_set_data(void* h, const double* txyz, int Vt, const int* ttris, int Ft, const double* sxyz, int Vs, const int* stris, int Fs,
+                           const double* input, const double* ref, int C) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        b->target = mesh_from(txyz, Vt, ttris, Ft);
+        b->source = mesh_from(sxyz, Vs, stris, Fs);
+        b->model->set_featurespace(std::make_shared<featurespace>(input, Vs, ref, Vt, C));
+        b->model->set_meshspace(b->target, b->source);
+    });
+}
+// CONTROL = ico(CPres) at RAD (src/mesh_registration.cpp:67-69) then model->Initialize(CONTROL) (:86)
+int msmhost_model_initialize(void* h, int cpres) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        newresampler::Mesh CONTROL = newresampler::make_mesh_from_icosa(cpres);
+        newresampler::recentre(CONTROL);
+        newresampler::true_rescale(CONTROL, RAD);
+        b->model->Initialize(CONTROL);
+    });
+}
+int msmhost_model_sizes(void* h, int* N, int* L, int* P, int* T) {
+    auto* b = (ModelBox*)h;
+    *N = b->model->getNumNodes(); *L = b->model->getNumLabels(); *P = b->model->getNumPairs(); *T = b->model->getNumTriplets();
+    return 0;
+}
+int msmhost_model_reset_meshspace(void* h, const double* sxyz) {  // src/mesh_registration.cpp:336
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        for (int i = 0; i < b->source.nvertices(); i++) b->source.set_coord(i, newresampler::Point(sxyz[3 * i], sxyz[3 * i + 1], sxyz[3 * i + 2]));
+        b->model->reset_meshspace(b->source);
+    });
+}
+int msmhost_model_reset_cpgrid(void* h, const double* cxyz) {  // :393
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        newresampler::Mesh g = b->model->get_CPgrid();
+        for (int i = 0; i < g.nvertices(); i++) g.set_coord(i, newresampler::Point(cxyz[3 * i], cxyz[3 * i + 1], cxyz[3 * i + 2]));
+        b->model->reset_CPgrid(g);
+    });
+}
+int msmhost_model_setup(void* h) { auto* b = (ModelBox*)h; return guard([&] { b->model->setupCostFunction(); }); }  // :337
+int msmhost_model_unary(void* h, double* out) {  // :347 computeUnaryCosts + the table
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        b->model->computeUnaryCosts();
+        const size_t n = (size_t)b->model->getNumNodes() * b->model->getNumLabels();
+        std::memcpy(out, b->model->getCostFunction()->getUnaryCosts(), n * sizeof(double));
+    });
+}
+int msmhost_model_get(void* h, double* cpgrid, double* labels, int* pairs, int* triplets) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        if (cpgrid) { auto c = b->model->get_CPgrid().coords(); std::memcpy(cpgrid, c.data(), c.size() * sizeof(double)); }
+        if (labels) {
+            const auto& l = b->model->get_labels();
+            for (size_t i = 0; i < l.size(); i++) { labels[3 * i] = l[i].X; labels[3 * i + 1] = l[i].Y; labels[3 * i + 2] = l[i].Z; }
+        }
+        if (pairs && b->model->getNumPairs()) std::memcpy(pairs, b->model->getPairs(), sizeof(int) * 2 * b->model->getNumPairs());
+        if (triplets && b->model->getNumTriplets()) std::memcpy(triplets, b->model->getTriplets(), sizeof(int) * 3 * b->model->getNumTriplets());
+    });
+}
+// per-element virtuals, batched: kind 0 unary (q[n][2]), 1 pairwise (q[n][3]), 2 triplet (q[n][4])
+int msmhost_model_costs(void* h, int kind, int n, const int* q, double* out) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+#pragma omp parallel for
+        for (int i = 0; i < n; i++) {
+            if (kind == 0) out[i] = b->model->computeUnaryCost(q[2 * i], q[2 * i + 1]);
+            else if (kind == 1) out[i] = b->model->computePairwiseCost(q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+            else out[i] = b->model->computeTripletCost(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+        }
+    });
+}
+int msmhost_model_set_labeling(void* h, const int* lab) {
+    auto* b = (ModelBox*)h;
+    std::memcpy(b->model->getLabeling(), lab, sizeof(int) * b->model->getNumNodes());
+    return 0;
+}
+int msmhost_model_get_labeling(void* h, int* lab) {
+    auto* b = (ModelBox*)h;
+    std::memcpy(lab, b->model->getLabeling(), sizeof(int) * b->model->getNumNodes());
+    return 0;
+}
+double msmhost_model_total(void* h) { auto* b = (ModelBox*)h; double v = 0; guard([&] { v = b->model->evaluateTotalCostSum(); }); return v; }
+int msmhost_model_apply_labeling(void* h, double* new_cpgrid) {  // :386
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        b->model->applyLabeling();
+        auto c = b->model->get_CPgrid().coords();
+        std::memcpy(new_cpgrid, c.data(), c.size() * sizeof(double));
+    });
+}
+// borrowed handle of the cost function's device context (device-resident table variants of the C ABI)
+void* msmhost_model_context(void* h) { return ((ModelBox*)h)->model->getNonLinearCostFunction()->context(); }
+int msmhost_model_triplet_moves(void* h, const int* labeling, int alpha, double* out) {
+    auto* b = (ModelBox*)h;
+    return guard([&] { b->model->getNonLinearCostFunction()->computeTripletMoves(labeling, alpha, out); });
+}
+
+#ifdef WITH_REF_OPTIM
+// ---- unmodified reference optimisers ------------------------------------------------------------------------------
+int ref_available() { return 1; }
+// src/mesh_registration.cpp:346-352
+int ref_fastpd_model(void* h, double* energy) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        b->model->computeUnaryCosts();
+        b->model->computePairwiseCosts();
+        FPD::FastPD opt(b->model, 100);
+        *energy = opt.run();
+        opt.getLabeling(b->model->getLabeling());
+    });
+}
+// :358
+int ref_fusion_model(void* h, int threads, double* energy) {
+    auto* b = (ModelBox*)h;
+    return guard([&] { *energy = Fusion::optimize(b->model, false, threads); });
+}
+int ref_fastpd_tables(int N, int L, int P, const int* pairs, const double* unary, const double* pairtab, int* labeling, double* energy) {
+    return guard([&] {
+        auto cf = std::make_shared<TableCostFunction>(N, L, P, 0, unary, pairtab, nullptr);
+        auto model = std::make_shared<TableModel>(N, L, P, pairs, 0, nullptr, cf);
+        cf->setPairs(const_cast<int*>(model->getPairs()));
+        FPD::FastPD opt(model, 100);
+        *energy = opt.run();
+        opt.getLabeling(labeling);
+    });
+}
+int ref_fusion_tables(int N, int L, int P, const int* pairs, int T, const int* triplets, const double* unary, const double* pairtab,
+                      const double* triptab, int threads, int* labeling, double* energy) {
+    return guard([&] {
+        auto cf = std::make_shared<TableCostFunction>(N, L, P, T, unary, pairtab, triptab);
+        auto model = std::make_shared<TableModel>(N, L, P, pairs, T, triplets, cf);
+        *energy = Fusion::optimize(model, false, threads);
+        std::memcpy(labeling, model->getLabeling(), sizeof(int) * N);
+    });
+}
+#endif
+
+}  // extern "C"

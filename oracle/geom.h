@@ -228,10 +228,12 @@ inline Mesh make_mesh_from_icosa(int level, double radius = RAD) {
     const int faces[20][3] = {{0, 11, 5}, {0, 5, 1},  {0, 1, 7},   {0, 7, 10}, {0, 10, 11}, {1, 5, 9}, {5, 11, 4},
                               {11, 10, 2}, {10, 7, 6}, {7, 1, 8},  {3, 9, 4},  {3, 4, 2},   {3, 2, 6}, {3, 6, 8},
                               {3, 8, 9},  {4, 9, 5},  {2, 4, 11},  {6, 2, 10}, {8, 6, 7},   {9, 8, 1}};
+    // the reference builds the unit icosphere and then calls true_rescale(m, RAD) (src/mesh_registration.cpp:67-69,
+    // src/DiscreteModel.cpp:93-94): subdivide at unit radius, rescale at the end
     for (auto& b : base) {
         Pt p(b[0], b[1], b[2]);
         p.normalize();
-        M.V.push_back(p * radius);
+        M.V.push_back(p);
     }
     for (auto& f : faces) M.F.push_back({f[0], f[1], f[2]});
     for (int l = 0; l < level; l++) {
@@ -242,7 +244,7 @@ inline Mesh make_mesh_from_icosa(int level, double radius = RAD) {
             if (it != mid.end()) return it->second;
             Pt p = M.V[a] + M.V[b];
             p.normalize();
-            M.V.push_back(p * radius);
+            M.V.push_back(p);
             int id = (int)M.V.size() - 1;
             mid[key] = id;
             return id;
@@ -258,6 +260,10 @@ inline Mesh make_mesh_from_icosa(int level, double radius = RAD) {
             NF.push_back({ab, bc, ca});
         }
         M.F.swap(NF);
+    }
+    for (auto& p : M.V) {  // true_rescale
+        p.normalize();
+        p = p * radius;
     }
     M.build_adjacency();
     return M;

@@ -134,6 +134,14 @@ def gpu_context(P, params=None, cfweight=None, multivariate=None, cliques="tripl
     return ctx
 
 
+def singular_nodes(P):
+    """Control points (numerically) antipodal to the label-grid centre: ROT[k] = rotation(centre -> CP_k) is a rotation
+    by pi about an undefined axis there (src/DiscreteModel.cpp:284-294 + [EXT] estimate_rotation_matrix), so every cost
+    touching such a node is noise in the reference itself.  A regular icosphere contains exactly one such CP."""
+    c = (P.cxyz @ P.centre) / (np.linalg.norm(P.cxyz, axis=1) * np.linalg.norm(P.centre))
+    return np.nonzero(c < -1 + 1e-9)[0]
+
+
 def rel_err(gpu, ref, floor):
     """|gpu-ref| / max(|ref|, floor): the tolerance form stated in SURVEY.md §7 (hard parts)."""
     gpu = np.asarray(gpu, np.float64); ref = np.asarray(ref, np.float64)

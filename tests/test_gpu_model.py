@@ -1,0 +1,111 @@
+"""GPU tests of the drop-in boundary: the host-side mirror classes (NonLinearSRegDiscreteModel + GPU-backed cost
+functions, msm_newmeshreg_b200/host/src) against the oracle's restatement of the same model glue, and the
+optimiser-equivalence tests: the reference's own, unmodified FastPD / Fusion(HOCR) optimisers (oracle/_ref) must return
+IDENTICAL labellings whether they are driven by the GPU-backed model or by the oracle's cost tables."""
+import numpy as np
+import pytest
+
+import problems as pb
+from oracle import pyorc, pyref
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(P, lib=None, **kw):
+    from msm_newmeshreg_b200 import host
+    pr = dict(pb.DEFAULT_PARAMS); pr.update(kw)
+    m = host.Model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=P.C > 1, _lib_override=lib, **pr)
+    m.set_data(P.txyz, P.ttris, P.sxyz, P.ttris, P.inp, P.ref)
+    m.initialize()
+    return m
+
+
+def test_model_glue_matches_oracle(built):
+    """Label grid, cliques, control grid and the unary table through the class interface."""
+    P = pb.make_problem(4, 2, 1, seed=31, warp=0.3)
+    m = _model(P, rmode=3)
+    m.setup()                                   # iteration 1: barycentre labels
+    assert (m.N, m.L, m.T) == (P.N, len(P.barycentres), P.T)
+    assert np.array_equal(m.labels(), P.barycentres) and np.array_equal(m.triplets(), P.triplets)
+    assert np.array_equal(m.cpgrid(), P.cxyz0)
+    cf = pb.oracle_costfunction(P); cf.get_source_data()
+    good = np.ones(P.N, bool); good[pb.singular_nodes(P)] = False
+    assert pb.rel_err(m.unary()[:, good], cf.unary_costs()[:, good], 1e-2).max() < 1e-5
+    q = np.array([[5, 3], [17, 0], [100, 18]], np.int32)
+    assert np.array_equal(m.costs("unary", q), m.unary()[q[:, 1], q[:, 0]])   # per-element virtual = table look-up
+    m.setup()                                   # iteration 2: vertex samples (src/DiscreteModel.cpp:215-220)
+    assert np.array_equal(m.labels(), P.samples)
+    mp = _model(P, rmode=1, dopt="FastPD")
+    mp.setup()
+    assert np.array_equal(mp.pairs(), P.pairs)
+    m.close(); mp.close()
+
+
+def test_apply_labeling(built):
+    P = pb.make_problem(3, 2, 1, seed=32, warp=0.2)
+    m = _model(P, rmode=3); m.setup()
+    lab = np.random.default_rng(0).integers(0, m.L, m.N).astype(np.int32)
+    m.set_labeling(lab)
+    new = m.apply_labeling()
+    expect = np.einsum("nij,nj->ni", P.rot, P.labels[lab])          # CP_k <- ROT[k] * labels[lab[k]]  (:238-243)
+    good = np.ones(P.N, bool); good[pb.singular_nodes(P)] = False
+    assert np.abs(new - expect)[good].max() < 1e-9
+    m.close()
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+def test_fastpd_labelling_identical(built):
+    """--dopt FastPD (src/mesh_registration.cpp:346-352): GPU-backed model vs oracle tables, same unmodified optimiser."""
+    P = pb.make_problem(4, 2, 1, seed=33, warp=0.3, deform_cp=0.1)
+    m = _model(P, lib=pyref.lib(), rmode=1, dopt="FastPD")
+    m.reset_cpgrid(P.cxyz)
+    m.setup()
+    lab_gpu, e_gpu = pyref.fastpd_model(m)
+    cf = pb.oracle_costfunction(P, params=dict(rmode=1), cliques="pairs"); cf.get_source_data()
+    lab_orc, e_orc = pyref.fastpd_tables(cf.unary_costs(), P.pairs, cf.pair_table())
+    assert np.array_equal(lab_gpu, lab_orc), f"{(lab_gpu != lab_orc).sum()} of {P.N} labels differ"
+    assert abs(e_gpu - e_orc) <= 1e-5 * abs(e_orc)
+    m.close()
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("C", [1, 4])
+def test_fusion_hocr_labelling_identical(built, C):
+    """--dopt HOCR with the strain regulariser (--regoption 3): Fusion::optimize -> ELC/HOCR -> inner FastPD."""
+    P = pb.make_problem(4, 2, C, seed=34, warp=0.3, deform_cp=0.1)
+    m = _model(P, lib=pyref.lib(), rmode=3, dopt="HOCR")
+    m.reset_cpgrid(P.cxyz)
+    m.setup()
+    lab_gpu, e_gpu = pyref.fusion_model(m, threads=4)
+    cf = pb.oracle_costfunction(P, params=dict(rmode=3)); cf.get_source_data()
+    lab_orc, e_orc = pyref.fusion_tables(cf.unary_costs(), P.triplets, cf.triplet_table(), threads=4)
+    assert np.array_equal(lab_gpu, lab_orc), f"{(lab_gpu != lab_orc).sum()} of {P.N} labels differ"
+    assert abs(e_gpu - e_orc) <= 1e-5 * abs(e_orc)
+    m.close()
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+def test_outer_iterations_labellings_identical(built):
+    """Two outer iterations of run_discrete_opt (src/mesh_registration.cpp:320-396) restated with the source mesh held
+    fixed (the source warp is a 'next' row): setupCostFunction -> HOCR -> applyLabeling -> reset_CPgrid, with
+    the label set alternating between barycentres and samples; labellings must agree at every iteration."""
+    P = pb.make_problem(4, 2, 1, seed=35, warp=0.3)
+    m = _model(P, lib=pyref.lib(), rmode=3, dopt="HOCR")
+    cp = P.cxyz0.copy()
+    for it in (1, 2):
+        m.setup()
+        lab_gpu, _ = pyref.fusion_model(m, threads=4)
+        Q = pb.make_problem(4, 2, 1, seed=35, warp=0.3, iteration=it)
+        Q.cxyz = cp; Q.rot = pyorc.rotations(Q.centre, cp)
+        cf = pb.oracle_costfunction(Q, params=dict(rmode=3)); cf.get_source_data()
+        lab_orc, _ = pyref.fusion_tables(cf.unary_costs(), Q.triplets, cf.triplet_table(), threads=4)
+        assert np.array_equal(lab_gpu, lab_orc), f"iteration {it}: {(lab_gpu != lab_orc).sum()} labels differ"
+        new_gpu = m.apply_labeling()
+        cp = np.einsum("nij,nj->ni", Q.rot, Q.labels[lab_orc])
+        cp *= 100.0 / np.linalg.norm(cp, axis=1, keepdims=True)
+        sing = pb.singular_nodes(Q)
+        keep = np.ones(P.N, bool); keep[sing] = False
+        assert np.abs(new_gpu - cp)[keep].max() < 1e-9
+        cp[sing] = new_gpu[sing]
+        m.reset_cpgrid(cp)
+    m.close()
