@@ -262,8 +262,9 @@ def main():
         seed = 1000 + 97 * rank + s
         S = Subject(txyz, ttris, C, seed, mvd)
         m = host.Model(sgres=args.cp_level + 2, cpres=args.cp_level, multivariate=C > 1, dopt="HOCR", threads=1, **PARAMS)
-        m.set_data(txyz, ttris, S.sxyz, ttris, S.inp, S.ref)
+        m.set_data(txyz, ttris, txyz, ttris, S.inp, S.ref)   # level start: source == undeformed template (_ORIG)
         m.initialize()
+        m.reset_meshspace(S.sxyz)                               # deformed source of the current outer iteration
         cxyz = smooth_warp(cxyz0, seed + 200, 0.1 * mvd)
         m.reset_cpgrid(cxyz)
         m.setup()
@@ -336,8 +337,9 @@ def main():
             models[s].reset_meshspace(sx.numpy())
             models[s].reset_cpgrid(cx.numpy())
             models[s].setup()                       # patch construction + unary table -> host double[L][N]
-            models[s].triplet_moves(lab_host, -1)   # -> host double[L][T][8]
+            models[s].triplet_moves(lab_host, -1, out=moves_host.numpy())   # -> pinned host double[L][T][8]
 
+    moves_host = torch.empty((L, T, 8), dtype=torch.float64).pin_memory()
     for _ in range(1):
         e2e_step()
     sync_all()

@@ -155,8 +155,10 @@ class Model:
         self._L.msmhost_model_context.restype = C.c_void_p
         return Context.from_handle(self._L.msmhost_model_context(self.h), self.N, self.L, self.T, self.P)
 
-    def triplet_moves(self, labeling, alpha):
+    def triplet_moves(self, labeling, alpha, out=None):
+        """`out`: optional caller-owned float64 buffer (e.g. pinned memory) of shape [L][T][8] / [T][8]."""
         labeling, p = _i(labeling)
-        out = np.empty((self.L, self.T, 8) if alpha < 0 else (self.T, 8))
+        if out is None:
+            out = np.empty((self.L, self.T, 8) if alpha < 0 else (self.T, 8))
         self._ck(self._L.msmhost_model_triplet_moves(self.h, p, int(alpha), out.ctypes.data_as(c_dp)))
         return out

@@ -115,43 +115,44 @@ private:
 class Mesh {  // A7 (container + adjacency; no I/O: on-disk formats stay outside the hot path)
 public:
     int nvertices() const { return (int)V_.size(); }
-    int ntriangles() const { return (int)F_.size(); }
+    int ntriangles() const { return (int)topo_->F.size(); }
     const Point& get_coord(int i) const { return V_[i]; }
     void set_coord(int i, const Point& p) { V_[i] = p; }
-    int get_triangle_vertexID(int t, int j) const { return F_[t][j]; }
-    Point get_triangle_vertex(int t, int j) const { return V_[F_[t][j]]; }
+    int get_triangle_vertexID(int t, int j) const { return topo_->F[t][j]; }
+    Point get_triangle_vertex(int t, int j) const { return V_[topo_->F[t][j]]; }
     Triangle get_triangle(int t) const {
-        Triangle T(V_[F_[t][0]], V_[F_[t][1]], V_[F_[t][2]], t);
-        for (int j = 0; j < 3; j++) T.set_vertex_no(j, F_[t][j]);
+        Triangle T(V_[topo_->F[t][0]], V_[topo_->F[t][1]], V_[topo_->F[t][2]], t);
+        for (int j = 0; j < 3; j++) T.set_vertex_no(j, topo_->F[t][j]);
         return T;
     }
-    std::vector<int>::const_iterator nbegin(int i) const { return nbr_[i].begin(); }
-    std::vector<int>::const_iterator nend(int i) const { return nbr_[i].end(); }
-    std::vector<int>::const_iterator tIDbegin(int i) const { return vtri_[i].begin(); }
-    std::vector<int>::const_iterator tIDend(int i) const { return vtri_[i].end(); }
-    int get_total_neighbours(int i) const { return (int)nbr_[i].size(); }
+    std::vector<int>::const_iterator nbegin(int i) const { return topo_->nbr[i].begin(); }
+    std::vector<int>::const_iterator nend(int i) const { return topo_->nbr[i].end(); }
+    std::vector<int>::const_iterator tIDbegin(int i) const { return topo_->vtri[i].begin(); }
+    std::vector<int>::const_iterator tIDend(int i) const { return topo_->vtri[i].end(); }
+    int get_total_neighbours(int i) const { return (int)topo_->nbr[i].size(); }
     int get_resolution() const { return resolution_; }
     double calculate_MaxVD() const {
         double mx = 0;
-        for (int i = 0; i < nvertices(); i++) for (int j : nbr_[i]) mx = std::max(mx, (V_[i] - V_[j]).norm());
+        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) mx = std::max(mx, (V_[i] - V_[j]).norm());
         return mx;
     }
     double calculate_MeanVD() const {
         double s = 0; long n = 0;
-        for (int i = 0; i < nvertices(); i++) for (int j : nbr_[i]) { s += (V_[i] - V_[j]).norm(); n++; }
+        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) { s += (V_[i] - V_[j]).norm(); n++; }
         return n ? s / n : 0;
     }
     std::vector<std::vector<double>> get_face_angles() const {
-        std::vector<std::vector<double>> a(F_.size());
+        std::vector<std::vector<double>> a(topo_->F.size());
         for (int t = 0; t < ntriangles(); t++) a[t] = get_triangle(t).get_angles();
         return a;
     }
     // construction
     void set(const double* xyz, int nv, const int* tris, int nf, int resolution = -1) {
+        topo_ = std::make_shared<Topo>();  // never mutate a topology another copy may share
         V_.resize(nv);
         for (int i = 0; i < nv; i++) V_[i] = Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
-        F_.resize(nf);
-        for (int t = 0; t < nf; t++) F_[t] = {tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]};
+        topo_->F.resize(nf);
+        for (int t = 0; t < nf; t++) topo_->F[t] = {tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]};
         resolution_ = resolution;
         build_adjacency();
     }
@@ -162,24 +163,29 @@ public:
     }
     std::vector<int> faces() const {
         std::vector<int> o((size_t)ntriangles() * 3);
-        for (int t = 0; t < ntriangles(); t++) for (int j = 0; j < 3; j++) o[3 * t + j] = F_[t][j];
+        for (int t = 0; t < ntriangles(); t++) for (int j = 0; j < 3; j++) o[3 * t + j] = topo_->F[t][j];
         return o;
     }
     // adjacency order: faces ascending; neighbours by first appearance over those faces
     void build_adjacency() {
-        nbr_.assign(V_.size(), {}); vtri_.assign(V_.size(), {});
-        for (int t = 0; t < ntriangles(); t++) for (int j = 0; j < 3; j++) vtri_[F_[t][j]].push_back(t);
+        topo_->nbr.assign(V_.size(), {}); topo_->vtri.assign(V_.size(), {});
+        for (int t = 0; t < ntriangles(); t++) for (int j = 0; j < 3; j++) topo_->vtri[topo_->F[t][j]].push_back(t);
         for (int v = 0; v < nvertices(); v++)
-            for (int t : vtri_[v])
+            for (int t : topo_->vtri[v])
                 for (int j = 0; j < 3; j++) {
-                    int u = F_[t][j];
-                    if (u != v && std::find(nbr_[v].begin(), nbr_[v].end(), u) == nbr_[v].end()) nbr_[v].push_back(u);
+                    int u = topo_->F[t][j];
+                    if (u != v && std::find(topo_->nbr[v].begin(), topo_->nbr[v].end(), u) == topo_->nbr[v].end()) topo_->nbr[v].push_back(u);
                 }
     }
     std::vector<Point> V_;
-    std::vector<std::array<int, 3>> F_;
 private:
-    std::vector<std::vector<int>> nbr_, vtri_;
+    // topology is immutable once set and shared between copies: the drivers copy meshes freely
+    // (reset_meshspace / reset_CPgrid take meshes by value semantics), only coordinates ever change
+    struct Topo {
+        std::vector<std::array<int, 3>> F;
+        std::vector<std::vector<int>> nbr, vtri;
+    };
+    std::shared_ptr<Topo> topo_ = std::make_shared<Topo>();
     int resolution_ = -1;
 };
 
