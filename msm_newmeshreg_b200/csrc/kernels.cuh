@@ -262,30 +262,34 @@ __global__ void __launch_bounds__(128) k_patch_binned(PatchArgs a, BinGrid g, in
 // exclusive scan of (counts + accepted) over the shard rows; also total and max.  Single CTA.
 __global__ void __launch_bounds__(1024) k_patch_scan(int n, const int* __restrict__ counts, const int* __restrict__ acc_off,
                                                      int* __restrict__ off, int* __restrict__ total_max) {
+    // each thread owns one contiguous segment: local sum, one block-wide scan of the 1024 partials, local rewrite
     __shared__ int s[1024];
-    __shared__ int s_carry, s_max;
+    __shared__ int s_max;
     const int tid = threadIdx.x;
-    if (tid == 0) { s_carry = 0; s_max = 0; }
+    const int seg = (n + 1023) / 1024;
+    const int b = min(n, tid * seg), e = min(n, b + seg);
+    if (tid == 0) s_max = 0;
+    int sum = 0, mx = 0;
+    for (int i = b; i < e; i++) {
+        const int c = counts[i] + (acc_off ? (acc_off[i + 1] - acc_off[i]) : 0);
+        sum += c; mx = max(mx, c);
+    }
+    s[tid] = sum;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        int i = base + tid;
-        int c = 0;
-        if (i < n) c = counts[i] + (acc_off ? (acc_off[i + 1] - acc_off[i]) : 0);
-        s[tid] = c;
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = (tid >= o) ? s[tid - o] : 0;
         __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            int v = (tid >= o) ? s[tid - o] : 0;
-            __syncthreads();
-            s[tid] += v;
-            __syncthreads();
-        }
-        if (i < n) off[i] = s_carry + s[tid] - c;
-        atomicMax(&s_max, c);
-        __syncthreads();
-        if (tid == 0) s_carry += s[1023];
+        s[tid] += v;
         __syncthreads();
     }
-    if (tid == 0) { off[n] = s_carry; total_max[0] = s_carry; total_max[1] = s_max; }
+    atomicMax(&s_max, mx);
+    int run = s[tid] - sum;
+    for (int i = b; i < e; i++) {
+        const int c = counts[i] + (acc_off ? (acc_off[i + 1] - acc_off[i]) : 0);
+        off[i] = run; run += c;
+    }
+    __syncthreads();
+    if (tid == 1023) { off[n] = s[1023]; total_max[0] = s[1023]; total_max[1] = s_max; }
 }
 
 // gather the packed per-patch sample streams (SoA over the global sample index) — coalesced reads in k_unary.
@@ -471,20 +475,27 @@ __global__ void __launch_bounds__(128) k_triplet_queries(TripArgs a, int n, cons
 // alpha >= 0: out[t][8]; alpha < 0: all labels, out[alpha][t][8].
 template <typename OutT>
 __global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const int* __restrict__ labeling, int alpha, OutT* __restrict__ out) {
+    // one thread per (alpha, triplet): the triangle constants and the six candidate corners (current / alpha label of
+    // each vertex) are formed once and shared by the 8 combinations
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nalpha = alpha < 0 ? a.L : 1;
-    if (gid >= (long long)nalpha * T * 8) return;
-    const int combo = (int)(gid & 7);
-    const long long rest = gid >> 3;
-    const int t = (int)(rest % T);
-    const int al = alpha < 0 ? (int)(rest / T) : alpha;
+    if (gid >= (long long)nalpha * T) return;
+    const int t = (int)(gid % T);
+    const int al = alpha < 0 ? (int)(gid / T) : alpha;
     int id[3]; TripGeom g;
     trip_load(a, t, id, g);
-    const int la = (combo & 4) ? al : labeling[id[0]];
-    const int lb = (combo & 2) ? al : labeling[id[1]];
-    const int lc = (combo & 1) ? al : labeling[id[2]];
-    out[gid] = (OutT)trip_cost(a.p, g, a.disp + ((size_t)id[0] * a.L + la) * 3, a.disp + ((size_t)id[1] * a.L + lb) * 3,
-                               a.disp + ((size_t)id[2] * a.L + lc) * 3);
+    double pc[3][3], pa[3][3];
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+        const double* c = a.disp + ((size_t)id[v] * a.L + labeling[id[v]]) * 3;
+        const double* n = a.disp + ((size_t)id[v] * a.L + al) * 3;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { pc[v][j] = c[j]; pa[v][j] = n[j]; }
+    }
+    OutT* o = out + gid * 8;
+#pragma unroll
+    for (int combo = 0; combo < 8; combo++)
+        o[combo] = (OutT)trip_cost(a.p, g, (combo & 4) ? pa[0] : pc[0], (combo & 2) ? pa[1] : pc[1], (combo & 1) ? pa[2] : pc[2]);
 }
 
 // full table: one CTA per triplet; displaced corners staged in shared memory; thread = (la,lb), loop lc;

@@ -26,7 +26,7 @@ struct HintDev {
     int node_off;           // (4^h - 1)/3
     const double* hdual;    // [20*4^h][9]
     const int* hnbr;        // [20*4^h][3]
-    const float* hT;        // [20*4^h][3][9]
+    const float4* hT;       // [20*4^h][3 edges][3 rows] : (T row, w of row 0 = neighbour face id as int bits)
 };
 
 // 20 base faces: dual basis rows (alpha = A.p, beta = B.p, gamma = C.p) and centre directions.
@@ -99,21 +99,46 @@ __device__ __forceinline__ int ico_descend(const IcoDev& ico, int base, T& al, T
 // Branch-free: the child is picked from the signs of (2x - s), the child's incoming multipliers come from one
 // 16-byte table read, and the value entering each product is |2x - s| for the child's own corner / the centre child
 // and x otherwise.
-__device__ __forceinline__ int ico_descend_from(const float4* __restrict__ mtab, int nlev, int n, float& al, float& be, float& ga) {
-#pragma unroll 1
-    for (int l = 0; l < nlev; l++) {
-        const float s = al + be + ga;
-        const float sa = fmaf(al, 2.f, -s), sb = fmaf(be, 2.f, -s), sc = fmaf(ga, 2.f, -s);
-        const bool ca = sa > 0.f, cb = !ca && sb > 0.f, cc = !ca && !cb && sc > 0.f;
-        const int child = ca ? 0 : (cb ? 1 : (cc ? 2 : 3));
-        n = 4 * n + 1 + child;
-        const float4 m = __ldg(mtab + n);
-        const float va = (cb | cc) ? al : fabsf(sa);
-        const float vb = (ca | cc) ? be : fabsf(sb);
-        const float vc = (ca | cb) ? ga : fabsf(sc);
-        al = va * m.x; be = vb * m.y; ga = vc * m.z;
-    }
+__device__ __forceinline__ void ico_descend_level(const float4* __restrict__ mtab, unsigned& n, float& al, float& be, float& ga) {
+    const float s = al + be + ga;
+    const float sa = fmaf(al, 2.f, -s), sb = fmaf(be, 2.f, -s), sc = fmaf(ga, 2.f, -s);
+    const bool ca = sa > 0.f, cb = sb > 0.f, cc = sc > 0.f;
+    // child: centre unless one of (2x - s) is positive; on (rounding-only) double positives the earlier corner wins
+    unsigned idx = 4u * n + 4u;
+    idx = cc ? idx - 1u : idx;
+    idx = cb ? 4u * n + 2u : idx;
+    idx = ca ? 4u * n + 1u : idx;
+    n = idx;
+    const float4 m = __ldg(mtab + idx);
+    const bool cb_ = cb && !ca, cc_ = cc && !ca && !cb;
+    const float va = (cb_ || cc_) ? al : fabsf(sa);
+    const float vb = (ca || cc_) ? be : fabsf(sb);
+    const float vc = (ca || cb_) ? ga : fabsf(sc);
+    al = va * m.x; be = vb * m.y; ga = vc * m.z;
+}
+
+template <int NLEV>
+__device__ __forceinline__ unsigned ico_descend_fixed(const float4* __restrict__ mtab, unsigned n, float& al, float& be, float& ga) {
+#pragma unroll
+    for (int l = 0; l < NLEV; l++) ico_descend_level(mtab, n, al, be, ga);
     return n;
+}
+
+__device__ __forceinline__ int ico_descend_from(const float4* __restrict__ mtab, int nlev, int n0, float& al, float& be, float& ga) {
+    unsigned n = (unsigned)n0;
+    switch (nlev) {  // uniform across the launch: fully unrolled bodies
+        case 1: n = ico_descend_fixed<1>(mtab, n, al, be, ga); break;
+        case 2: n = ico_descend_fixed<2>(mtab, n, al, be, ga); break;
+        case 3: n = ico_descend_fixed<3>(mtab, n, al, be, ga); break;
+        case 4: n = ico_descend_fixed<4>(mtab, n, al, be, ga); break;
+        case 5: n = ico_descend_fixed<5>(mtab, n, al, be, ga); break;
+        case 6: n = ico_descend_fixed<6>(mtab, n, al, be, ga); break;
+        case 7: n = ico_descend_fixed<7>(mtab, n, al, be, ga); break;
+        default:
+#pragma unroll 1
+            for (int l = 0; l < nlev; l++) ico_descend_level(mtab, n, al, be, ga);
+    }
+    return (int)n;
 }
 
 // Visibility walk on the level-h faces: cross the edge opposite the most negative corner coordinate.
@@ -122,11 +147,13 @@ __device__ __forceinline__ int ico_walk(const HintDev& hd, int face, float& al, 
         const float mn = fminf(al, fminf(be, ga));
         if (mn >= 0.f) break;
         const int e = (al == mn) ? 0 : ((be == mn) ? 1 : 2);
-        const float* T = hd.hT + ((size_t)face * 3 + e) * 9;
-        const float x = __ldg(T + 0) * al + __ldg(T + 1) * be + __ldg(T + 2) * ga;
-        const float y = __ldg(T + 3) * al + __ldg(T + 4) * be + __ldg(T + 5) * ga;
-        const float z = __ldg(T + 6) * al + __ldg(T + 7) * be + __ldg(T + 8) * ga;
-        face = __ldg(hd.hnbr + face * 3 + e);
+        // three 16-byte rows per (face, edge): the 3x3 change of corner coordinates; row 0 carries the neighbour id
+        const float4* T = hd.hT + (unsigned)(face * 3 + e) * 3u;
+        const float4 r0 = __ldg(T), r1 = __ldg(T + 1), r2 = __ldg(T + 2);
+        const float x = r0.x * al + r0.y * be + r0.z * ga;
+        const float y = r1.x * al + r1.y * be + r1.z * ga;
+        const float z = r2.x * al + r2.y * be + r2.z * ga;
+        face = __float_as_int(r0.w);
         al = x; be = y; ga = z;
     }
     return face;

@@ -276,7 +276,13 @@ int ensure_hint_level(msm_ctx* ctx) {
     std::vector<double> hdual, hT;
     std::vector<int> hnbr;
     ctx->ico.build_hint_level(h, hdual, hnbr, hT);
-    std::vector<float> hTf(hT.begin(), hT.end());
+    std::vector<float> hTf(hnbr.size() * 12, 0.f);   // per (face, edge): 3 rows of float4
+    for (size_t fe = 0; fe < hnbr.size(); fe++) {
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++) hTf[fe * 12 + 4 * r + c] = (float)hT[fe * 9 + 3 * r + c];
+        int nb = hnbr[fe];
+        std::memcpy(&hTf[fe * 12 + 3], &nb, 4);
+    }
     if (upload(ctx, ctx->d_hdual, hdual.data(), hdual.size())) return 1;
     if (upload(ctx, ctx->d_hnbr, hnbr.data(), hnbr.size())) return 1;
     if (upload(ctx, ctx->d_hT, hTf.data(), hTf.size())) return 1;
@@ -292,7 +298,7 @@ HintDev hint_dev(const msm_ctx* ctx) {
     d.node_off = (d.nf_per_base - 1) / 3;
     d.hdual = ctx->d_hdual.as<double>();
     d.hnbr = ctx->d_hnbr.as<int>();
-    d.hT = ctx->d_hT.as<float>();
+    d.hT = ctx->d_hT.as<float4>();
     return d;
 }
 
@@ -886,7 +892,7 @@ int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float*
     if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
     const long long n = (long long)(alpha < 0 ? ctx->L : 1) * ctx->Tn * 8;
     Timer tm(ctx, "triplet_moves");
-    k_triplet_moves<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, d_labeling, alpha, d_out);
+    k_triplet_moves<float><<<(unsigned)((n / 8 + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, d_labeling, alpha, d_out);
     KLAUNCH_CHECK();
     return 0;
 }
@@ -903,7 +909,7 @@ int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out)
     CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timer tm(ctx, "triplet_moves");
-        k_triplet_moves<double><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha,
+        k_triplet_moves<double><<<(unsigned)((n / 8 + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha,
                                                                                    ctx->d_scratch2.as<double>());
         KLAUNCH_CHECK();
     }

@@ -139,16 +139,17 @@ __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
     const int l0 = g * a.Lg, l1 = min(a.L, l0 + a.Lg), nl = l1 - l0;
     const int s0 = a.off[row], P = a.off[row + 1] - s0;
     const int tid = threadIdx.x;
-    // smem carve: r[3][P] | c[3][P] | a[CP_][P] | w[CP_][P] | lab[Lg][12] | tbuf[Lg][P]
-    float* rx = smem; float* ry = rx + P; float* rz = ry + P;
-    float* cx = rz + P; float* cy = cx + P; float* cz = cy + P;
-    float* sa = cz + P; float* sw = sa + CP_ * P;
-    float* sK = sw + CP_ * P;
-    float* tb = sK + a.Lg * 12;
+    // smem carve (16-byte aligned pieces first): lab[Lg][12] | rc4[P] = (rx,ry,rz,cx) | c2[P] = (cy,cz) | a[CP_][P] |
+    // w[CP_][P] | tbuf[Lg][P]
+    float* sK = smem;
+    float4* rc4 = reinterpret_cast<float4*>(sK + a.Lg * 12);
+    float2* c2 = reinterpret_cast<float2*>(rc4 + P);
+    float* sa = reinterpret_cast<float*>(c2 + P); float* sw = sa + CP_ * P;
+    float* tb = sw + CP_ * P;
 
     for (int i = tid; i < P; i += 256) {
-        rx[i] = a.px[s0 + i]; ry[i] = a.py[s0 + i]; rz[i] = a.pz[s0 + i];
-        cx[i] = a.pcx[s0 + i]; cy[i] = a.pcy[s0 + i]; cz[i] = a.pcz[s0 + i];
+        rc4[i] = make_float4(a.px[s0 + i], a.py[s0 + i], a.pz[s0 + i], a.pcx[s0 + i]);
+        c2[i] = make_float2(a.pcy[s0 + i], a.pcz[s0 + i]);
 #pragma unroll
         for (int c = 0; c < CP_; c++) {
             sa[c * P + i] = a.pa[(size_t)c * a.total + s0 + i];
@@ -169,17 +170,20 @@ __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
     for (int j = tid; j < items; j += 256) {
         const int l = (int)(((float)j + 0.5f) * invP);
         const int i = j - l * P;
-        const float x = rx[i], y = ry[i], z = rz[i];
-        const float* M = sK + l * 12;
-        float al = cx[i] + (M[9] + (M[0] * x + M[1] * y + M[2] * z));
-        float be = cy[i] + (M[10] + (M[3] * x + M[4] * y + M[5] * z));
-        float ga = cz[i] + (M[11] + (M[6] * x + M[7] * y + M[8] * z));
+        const float4 rc = rc4[i];
+        const float2 cc = c2[i];
+        const float x = rc.x, y = rc.y, z = rc.z;
+        const float4* M = reinterpret_cast<const float4*>(sK + l * 12);
+        const float4 m0 = M[0], m1 = M[1], m2 = M[2];   // (M00 M01 M02 M10) (M11 M12 M20 M21) (M22 g0 g1 g2)
+        float al = rc.w + (m2.y + (m0.x * x + m0.y * y + m0.z * z));
+        float be = cc.x + (m2.z + (m0.w * x + m1.x * y + m1.y * z));
+        float ga = cc.y + (m2.w + (m1.z * x + m1.w * y + m2.x * z));
         int face = face0;
         if (fminf(al, fminf(be, ga)) < 0.f) face = ico_walk(a.hint, face0, al, be, ga);
         const int base = face >> hshift;
         const int n = ico_descend_from(mtab, nlev, node_off + (face - (base << hshift)), al, be, ga);
         const int leaf = base * nleaf + (n - leaf_off);
-        const float inv = 1.0f / (al + be + ga);
+        const float inv = __fdividef(1.0f, al + be + ga);
         if (CQ == 0) {
             // face-packed (f0_hi, f0_lo, f1-f0, f2-f0): t - tref = (f0_hi - tref) + f0_lo + wb (f1-f0) + wc (f2-f0)
             const float4 f = __ldg(reinterpret_cast<const float4*>(a.face_feat) + leaf);
