@@ -186,6 +186,78 @@ def oracle_sample(data_level, cp_level, C, rows, threads, seed=1000, steps=1, wa
                 evals_per_s_resident=evals / (tu + tt), evals_per_s_e2e=evals / (tp + tu + tt))
 
 
+# ---------------------------------------------------------------------------------------------- CP-sharded mode
+def bench_cp_sharded(args, rank, world, local, C, metric, unit):
+    """ONE HCP-scale registration (ico7 / ico5): control points and triplets split into contiguous ranges over the GPUs
+    (SURVEY.md §8e rows 1-2), every GPU holds the replicated meshes, table slices gathered with one NCCL all_gather each
+    per step (never inside a per-label loop).  Strong scaling: total work fixed."""
+    import torch
+    import torch.distributed as dist
+    from msm_newmeshreg_b200 import host, sharding
+    txyz, ttris = host.icosphere(args.data_level)
+    cxyz0, ctris = host.icosphere(args.cp_level)
+    mvd = float(np.linalg.norm(cxyz0[ctris[:, 0]] - cxyz0[ctris[:, 1]], axis=1).mean())
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    S = Subject(txyz, ttris, C, 1000, mvd)                       # the same subject on every rank (replicated meshes)
+    m = host.Model(sgres=args.cp_level + 2, cpres=args.cp_level, multivariate=C > 1, dopt="HOCR", threads=1, **PARAMS)
+    m.set_data(txyz, ttris, txyz, ttris, S.inp, S.ref)
+    m.initialize()
+    m.reset_meshspace(S.sxyz)
+    m.reset_cpgrid(smooth_warp(cxyz0, 1200, 0.1 * mvd))
+    m.setup()
+    N, L, T = m.N, m.L, m.T
+    ctx = m.context()
+    ctx.set_stream(stream.cuda_stream)
+    k0, k1 = sharding.shard_range(N, rank, world)
+    t0, t1 = sharding.shard_range(T, rank, world)
+    ctx.set_shard(k0, k1)
+    ctx.build_patches()
+    lab_dev = torch.from_numpy(np.random.default_rng(7).integers(0, L, N).astype(np.int32)).cuda()
+    d_unary = torch.empty((L, k1 - k0), dtype=torch.float32, device="cuda")
+    d_moves = torch.empty((L, (t1 - t0) * 8), dtype=torch.float32, device="cuda")
+
+    def step():
+        ctx.unary_table_dev(d_unary.data_ptr())
+        ctx.triplet_moves_range_dev(lab_dev.data_ptr(), -1, t0, t1, d_moves.data_ptr())
+        U = sharding.allgather_label_major(d_unary, N)
+        M = sharding.allgather_label_major(d_moves, T, unit=8)
+        return U, M
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        U, M = step()
+    sync_all()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        U, M = step()
+    e1.record(stream)
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    evals = N * L + L * T * 8
+    checksum = float(U.double().sum().item()), float(M.double().sum().item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": metric, "value": evals / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (unary) / f64 (triplet)", "data": "synthetic",
+            "config": {"workload": f"C3 CP-sharded: ONE ico{args.data_level}/ico{args.cp_level} registration, control points and triplets "
+                                   f"split over {world} GPU(s), unary [L][N] and fusion-move [L][T][8] tables gathered with NCCL all_gather",
+                       "N": N, "L": L, "T": T, "gathered_bytes_per_step": 4 * (L * N + L * T * 8),
+                       "l2": "single subject: inputs are L2 resident between steps (mode used to show the sharded path, not the headline)"},
+            "gpu_launches": int(ctx.launch_count() - launches0), "checksum": checksum}))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -198,6 +270,9 @@ def main():
     ap.add_argument("--cp-level", type=int, default=5)
     ap.add_argument("--channels", type=int, default=1)
     ap.add_argument("--cpu-rows", type=int, default=1024, help="control points in the bounded CPU sample")
+    ap.add_argument("--mode", default="subjects", choices=["subjects", "cp"],
+                    help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
+                         "and triplets sharded over the GPUs, table slices all-gathered with NCCL (strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -247,6 +322,8 @@ def main():
         dist.barrier()
     from msm_newmeshreg_b200 import host
 
+    if args.mode == "cp":
+        return bench_cp_sharded(args, rank, world, local, C, metric, unit)
     B = args.subjects_per_gpu
     txyz, ttris = host.icosphere(args.data_level)
     cxyz0, ctris = host.icosphere(args.cp_level)

@@ -114,6 +114,8 @@ int msm_triplet_table(msm_ctx* ctx, int t0, int t1, float* out);
 int msm_triplet_table_dev(msm_ctx* ctx, int t0, int t1, float* d_out);
 int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out);
 int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float* d_out);
+/* Multi-GPU: the same for the triplet shard [t0,t1): d_out float[L or 1][t1-t0][8]. */
+int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, float* d_out);
 
 /* computePairwiseCosts (src/DiscreteCostFunction.cpp:256-304): out float[P][L][L] in the reference layout. */
 int msm_pair_table(msm_ctx* ctx, float* out);

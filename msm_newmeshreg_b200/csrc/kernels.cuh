@@ -444,6 +444,7 @@ struct TripArgs {
     DevParams p;
     int L;
     int group_N, group_T;            // per-subject sizes (group mode)
+    int t_off;                       // first triplet of a sharded moves launch
     const int* trip;                 // [T][3]
     const double* cp;                // [N][3] current
     const double* orig;              // [N or N_subj][3]
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const 
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int nalpha = alpha < 0 ? a.L : 1;
     if (gid >= (long long)nalpha * T) return;
-    const int t = (int)(gid % T);
+    const int t = a.t_off + (int)(gid % T);   // T = number of triplets of this launch (a shard [t_off, t_off+T))
     const int al = alpha < 0 ? (int)(gid / T) : alpha;
     int id[3]; TripGeom g;
     trip_load(a, t, id, g);

@@ -307,6 +307,7 @@ TripArgs trip_args(msm_ctx* ctx) {
     a.p = dev_params(ctx);
     a.L = ctx->L;
     a.group_N = ctx->N_subj; a.group_T = ctx->T_subj;
+    a.t_off = 0;
     a.trip = ctx->d_trip.as<int>();
     a.cp = ctx->d_cp.as<double>();
     a.orig = ctx->d_orig.as<double>();
@@ -886,15 +887,23 @@ int msm_triplet_table(msm_ctx* ctx, int t0, int t1, float* out) {
     return 0;
 }
 
-int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float* d_out) {
+int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, float* d_out) {
     CK(cudaSetDevice(ctx->device));
     if (check_triplets(ctx)) return 1;
     if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
-    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * ctx->Tn * 8;
+    if (t0 < 0 || t1 > ctx->Tn || t0 > t1) FAIL("msm_triplet_moves: bad triplet range");
+    if (t0 == t1) return 0;
+    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * (t1 - t0);
+    TripArgs a = trip_args(ctx);
+    a.t_off = t0;
     Timer tm(ctx, "triplet_moves");
-    k_triplet_moves<float><<<(unsigned)((n / 8 + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, d_labeling, alpha, d_out);
+    k_triplet_moves<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, t1 - t0, d_labeling, alpha, d_out);
     KLAUNCH_CHECK();
     return 0;
+}
+
+int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float* d_out) {
+    return msm_triplet_moves_range_dev(ctx, d_labeling, alpha, 0, ctx->Tn, d_out);
 }
 
 int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out) {

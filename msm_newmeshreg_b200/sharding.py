@@ -23,9 +23,10 @@ def subjects_of_rank(n_subjects, rank, world):
     return list(range(rank, n_subjects, world))
 
 
-def allgather_label_major(local, n, group=None):
-    """All-gather per-rank table slices local[L, n_r] (label-major rows, this rank's contiguous units as columns)
-    into the reference layout [L, n] (unary[label*N + node], src/DiscreteCostFunction.cpp:312).
+def allgather_label_major(local, n, group=None, unit=1):
+    """All-gather per-rank table slices local[L, n_r*unit] (label-major rows, this rank's contiguous units as columns,
+    `unit` values per unit) into the reference layout [L, n*unit] (unary[label*N + node], src/DiscreteCostFunction.cpp:312;
+    fusion-move tables [L][T][8] use unit=8).
 
     Works on CUDA tensors (NCCL) and CPU tensors (gloo).  Slices are padded to the largest shard so that one
     fixed-size all_gather suffices."""
@@ -35,7 +36,7 @@ def allgather_label_major(local, n, group=None):
     if world == 1:
         return local
     L = local.shape[0]
-    sizes = shard_sizes(n, world)
+    sizes = [s * unit for s in shard_sizes(n, world)]
     mx = max(sizes)
     send = torch.zeros((L, mx), dtype=local.dtype, device=local.device)
     send[:, : local.shape[1]] = local

@@ -1,44 +1,34 @@
-"""Scratch GPU debugging (not a pytest file)."""
+"""Scratch GPU debugging / timing breakdown of the end-to-end host path (not a pytest file)."""
 import os
 import sys
+import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-import problems as pb  # noqa: E402
-from oracle import pyorc, pyref  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
 from msm_newmeshreg_b200 import host  # noqa: E402
 
-P = pb.make_problem(4, 2, 1, seed=34, warp=0.3, deform_cp=0.1)
-pr = dict(pb.DEFAULT_PARAMS); pr.update(rmode=3, dopt="HOCR")
-m = host.Model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, _lib_override=pyref.lib(), **pr)
-m.set_data(P.txyz, P.ttris, P.sxyz, P.ttris, P.inp, P.ref)
+txyz, ttris = host.icosphere(7)
+cxyz0, ctris = host.icosphere(5)
+mvd = float(np.linalg.norm(cxyz0[ctris[:, 0]] - cxyz0[ctris[:, 1]], axis=1).mean())
+S = bench.Subject(txyz, ttris, 1, 1000, mvd)
+m = host.Model(sgres=7, cpres=5, multivariate=False, dopt="HOCR", threads=1, **bench.PARAMS)
+m.set_data(txyz, ttris, txyz, ttris, S.inp, S.ref)
 m.initialize()
-print("labels equal", np.array_equal(m.labels() if m.L else None, P.barycentres) if m.L else "L=0 before setup")
-m.reset_cpgrid(P.cxyz)
+m.reset_meshspace(S.sxyz)
+cxyz = bench.smooth_warp(cxyz0, 1200, 0.1 * mvd)
+m.reset_cpgrid(cxyz)
 m.setup()
-print("labels equal", np.array_equal(m.labels(), P.barycentres), np.abs(m.labels() - P.barycentres).max())
-print("triplets equal", np.array_equal(m.triplets(), P.triplets), "cpgrid equal", np.array_equal(m.cpgrid(), P.cxyz), np.abs(m.cpgrid() - P.cxyz).max())
-cf = pb.oracle_costfunction(P, params=dict(rmode=3)); cf.get_source_data()
-Uo = cf.unary_costs(); Ug = m.unary()
-print("unary max abs diff", np.abs(Ug - Uo).max())
-TT = cf.triplet_table()
-L = m.L
-q = np.array([[t, a, b, c] for t in range(0, P.T, 7) for a in range(0, L, 3) for b in range(0, L, 4) for c in range(0, L, 5)], np.int32)
-tg = m.costs("triplet", q)
-to = TT[q[:, 0], q[:, 1], q[:, 2], q[:, 3]]
-e = pb.rel_err(tg, to, 1e-4)
-print("triplet lookups max rel", e.max(), "max abs", np.abs(tg - to).max())
-lab_orc, e_orc = pyref.fusion_tables(Uo, P.triplets, TT, threads=4)
-lab_orc1, e_orc1 = pyref.fusion_tables(Uo, P.triplets, TT, threads=1)
-print("oracle fusion threads 4 vs 1 labels differ:", (lab_orc != lab_orc1).sum(), e_orc, e_orc1)
-# GPU tables through the table path
 ctx = m.context()
-TTg = ctx.triplet_table().astype(np.float64)
-lab_gt, e_gt = pyref.fusion_tables(Ug, P.triplets, TTg, threads=1)
-print("gpu tables (table path) vs oracle labels differ:", (lab_gt != lab_orc1).sum(), e_gt)
-TTo32 = TT.astype(np.float32).astype(np.float64)
-lab_o32, e_o32 = pyref.fusion_tables(Uo, P.triplets, TTo32, threads=1)
-print("oracle tables rounded to f32 vs oracle labels differ:", (lab_o32 != lab_orc1).sum(), e_o32)
-lab_gpu, e_gpu = pyref.fusion_model(m, threads=1)
-print("gpu model path vs oracle labels differ:", (lab_gpu != lab_orc1).sum(), e_gpu, " vs gpu table path:", (lab_gpu != lab_gt).sum())
+ctx.set_timing(1)
+lab = np.random.default_rng(7).integers(0, m.L, m.N).astype(np.int32)
+out = np.empty((m.L, m.T, 8))
+for rep in range(3):
+    t0 = time.perf_counter(); m.reset_meshspace(S.sxyz); t1 = time.perf_counter()
+    m.reset_cpgrid(cxyz); t2 = time.perf_counter()
+    m.setup(); t3 = time.perf_counter()
+    m.triplet_moves(lab, -1, out=out); t4 = time.perf_counter()
+    print(f"rep {rep}: reset_meshspace {1e3 * (t1 - t0):.2f} ms, reset_cpgrid {1e3 * (t2 - t1):.2f}, setup {1e3 * (t3 - t2):.2f} "
+          f"(patches family {ctx.last_kernel_ms('patches'):.2f}, label_rot {ctx.last_kernel_ms('label_rot'):.3f}, unary {ctx.last_kernel_ms('unary'):.3f}), "
+          f"triplet_moves {1e3 * (t4 - t3):.2f} (kernel {ctx.last_kernel_ms('triplet_moves'):.3f})")
