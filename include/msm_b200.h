@@ -136,6 +136,14 @@ int msm_group_pair_moves(msm_ctx* ctx, const int* labeling, int alpha, double* o
  * in that triangle's vertex order. */
 int msm_locate(msm_ctx* ctx, const double* pts, int M, int* tri, double* w);
 
+/* newresampler::barycentric_mesh_interpolation(SPH_up, SPH_low_init, SPH_low_final) ([EXT] A8; call sites
+ * src/mesh_registration.cpp:390 (warp the source by the control-grid update), :305-306 (level transition),
+ * src/DiscreteModel.h:123): every point is located in the START mesh (any closed spherical triangle mesh, deformed or
+ * not), and moved to the same barycentric combination of the END mesh's vertices, pushed back to `radius`.
+ * tri_out / w_out (optional): located triangle and weights in that triangle's vertex order. */
+int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* from_xyz, int V, const int* tris, int F,
+                         const double* to_xyz, double radius, double* out, int* tri_out, double* w_out);
+
 /* evaluateTotalCostSum (src/DiscreteCostFunction.cpp:41-70) from the device tables of the last *_table calls:
  * sums[0..2] = unary, pairwise, triplet; requires msm_unary_table(_dev) to have run. */
 int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]);

@@ -29,7 +29,7 @@ EXPORTS = [
     "msm_unary_table", "msm_unary_table_dev", "msm_triplet_costs", "msm_triplet_table", "msm_triplet_table_dev", "msm_triplet_moves",
     "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count",
     "msm_set_timing", "msm_last_kernel_ms", "msm_timing_collect", "msm_set_group_patches", "msm_group_pair_costs",
-    "msm_group_pair_moves",
+    "msm_group_pair_moves", "msm_mesh_interpolate",
 ]
 
 _lib = None
@@ -240,6 +240,19 @@ class Context:
         tri = np.empty(len(pts), np.int32); w = np.empty((len(pts), 3), np.float64)
         self._ck(lib().msm_locate(self._h, pp, len(pts), tri.ctypes.data_as(c_ip), w.ctypes.data_as(c_dp)))
         return tri, w
+
+    def mesh_interpolate(self, pts, from_xyz, tris, to_xyz, radius=100.0, details=False):
+        pts, pp = _d(pts); from_xyz, pf = _d(from_xyz); tris, pt = _i(tris); to_xyz, po = _d(to_xyz)
+        assert to_xyz.shape == from_xyz.shape
+        out = np.empty((len(pts), 3))
+        if details:
+            tri = np.empty(len(pts), np.int32); w = np.empty((len(pts), 3))
+            self._ck(lib().msm_mesh_interpolate(self._h, pp, len(pts), pf, len(from_xyz), pt, len(tris), po, C.c_double(radius),
+                                                out.ctypes.data_as(c_dp), tri.ctypes.data_as(c_ip), w.ctypes.data_as(c_dp)))
+            return out, tri, w
+        self._ck(lib().msm_mesh_interpolate(self._h, pp, len(pts), pf, len(from_xyz), pt, len(tris), po, C.c_double(radius),
+                                            out.ctypes.data_as(c_dp), None, None))
+        return out
 
     def total_cost(self, labeling):
         labeling, pl = _i(labeling); s = (C.c_double * 3)()

@@ -195,6 +195,22 @@ __device__ __forceinline__ void rodrigues_minus_identity(const double a_[3], con
     double theta = atan2(s, c);
 #pragma unroll
     for (int i = 0; i < 9; i++) K[i] = 0.0;
+    if (s < 1e-12 && c < 0.0) {
+        // antiparallel: rotation by pi about a x e, e = coordinate axis of a's smallest component (the convention shared
+        // with the host mirror and the oracle; the reference formula degenerates here).  R - I = 2 (u u^T - I).
+        const double ax = fabs(a[0]), ay = fabs(a[1]), az = fabs(a[2]);
+        double u[3];
+        if (ax <= ay && ax <= az) { u[0] = 0.0; u[1] = a[2]; u[2] = -a[1]; }        // a x (1,0,0)
+        else if (ay <= az) { u[0] = -a[2]; u[1] = 0.0; u[2] = a[0]; }               // a x (0,1,0)
+        else { u[0] = a[1]; u[1] = -a[0]; u[2] = 0.0; }                            // a x (0,0,1)
+        const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        u[0] /= nu; u[1] /= nu; u[2] /= nu;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) K[3 * i + j] = 2.0 * u[i] * u[j] - (i == j ? 2.0 : 0.0);
+        return;
+    }
     if (fabs(theta) < 1e-8 || s == 0.0) return;
     double kx = k[0] / s, ky = k[1] / s, kz = k[2] / s;
     // 1 - cos(theta) = s^2 / (1 + c) avoids cancellation for small angles

@@ -12,8 +12,11 @@
 #include <string>
 #include <vector>
 
+#include <array>
+
 #include "ico_hierarchy.h"
 #include "kernels.cuh"
+#include "meshwarp.cuh"
 
 using namespace msm;
 
@@ -112,6 +115,8 @@ struct msm_ctx {
     DevBuf d_cell_counts, d_cell_start, d_cell_fill, d_cell_of, d_sorted;  // voxel grid of the source vertices
     DevBuf d_pcx, d_pcy, d_pcz, d_hint_face, d_lab12, d_tref;  // k_unary_setup outputs
     int pack_cp = 0;
+
+    DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
 
     // outputs / scratch
     DevBuf d_unary, d_scratch, d_scratch2;
@@ -1040,6 +1045,79 @@ int msm_locate(msm_ctx* ctx, const double* pts, int M, int* tri, double* w) {
     }
     CK(cudaMemcpyAsync(tri, d_tri, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (w) CK(cudaMemcpyAsync(w, d_w, (size_t)M * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// barycentric_mesh_interpolation ([EXT] A8; src/mesh_registration.cpp:390,305-306; src/DiscreteModel.h:123)
+int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* from_xyz, int V, const int* tris, int F, const double* to_xyz,
+                         double radius, double* out, int* tri_out, double* w_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (M <= 0) return 0;
+    if (V <= 0 || F <= 0) FAIL("msm_mesh_interpolate: empty mesh");
+    // voxel grid over unit directions, cell ~ mean edge; each triangle goes to every cell its (bulge-expanded) box touches
+    std::vector<double> u((size_t)V * 3);
+    for (int i = 0; i < V; i++) {
+        const double n = std::sqrt(from_xyz[3 * i] * from_xyz[3 * i] + from_xyz[3 * i + 1] * from_xyz[3 * i + 1] + from_xyz[3 * i + 2] * from_xyz[3 * i + 2]);
+        if (!(n > 0)) FAIL("msm_mesh_interpolate: vertex at the origin");
+        for (int d = 0; d < 3; d++) u[3 * i + d] = from_xyz[3 * i + d] / n;
+    }
+    double mean_edge = 0;
+    for (int t = 0; t < F; t++) {
+        for (int j = 0; j < 3; j++)
+            if (tris[3 * t + j] < 0 || tris[3 * t + j] >= V) FAIL("msm_mesh_interpolate: triangle index out of range");
+        const double* a = &u[3 * tris[3 * t]]; const double* b = &u[3 * tris[3 * t + 1]];
+        mean_edge += std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+    }
+    mean_edge /= F;
+    const int G = std::max(4, std::min(192, (int)std::floor(2.0 / std::max(mean_edge, 1e-6))));
+    const double h = 2.0 / G;
+    auto cellc = [&](double x) { return std::max(0, std::min(G - 1, (int)std::floor((x + 1.0) / h))); };
+    std::vector<int> start((size_t)G * G * G + 1, 0);
+    std::vector<std::array<int, 6>> box(F);
+    for (int t = 0; t < F; t++) {
+        const double* a = &u[3 * tris[3 * t]]; const double* b = &u[3 * tris[3 * t + 1]]; const double* c = &u[3 * tris[3 * t + 2]];
+        auto d2 = [](const double* x, const double* y) { return (x[0] - y[0]) * (x[0] - y[0]) + (x[1] - y[1]) * (x[1] - y[1]) + (x[2] - y[2]) * (x[2] - y[2]); };
+        const double emax2 = std::max(d2(a, b), std::max(d2(b, c), d2(c, a)));
+        const double sag = 1.0 - std::sqrt(std::max(0.0, 1.0 - emax2 / 3.0)) + 1e-9;
+        for (int d = 0; d < 3; d++) {
+            box[t][d] = cellc(std::min(a[d], std::min(b[d], c[d])) - sag);
+            box[t][3 + d] = cellc(std::max(a[d], std::max(b[d], c[d])) + sag);
+        }
+        for (int x = box[t][0]; x <= box[t][3]; x++)
+            for (int y = box[t][1]; y <= box[t][4]; y++)
+                for (int z = box[t][2]; z <= box[t][5]; z++) start[((size_t)x * G + y) * G + z + 1]++;
+    }
+    for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+    std::vector<int> items(start.back()), fill(start.begin(), start.end() - 1);
+    for (int t = 0; t < F; t++)
+        for (int x = box[t][0]; x <= box[t][3]; x++)
+            for (int y = box[t][1]; y <= box[t][4]; y++)
+                for (int z = box[t][2]; z <= box[t][5]; z++) items[fill[((size_t)x * G + y) * G + z]++] = t;
+    if (upload(ctx, ctx->d_w_start, start.data(), start.size())) return 1;
+    if (upload(ctx, ctx->d_w_items, items.data(), items.size())) return 1;
+    if (upload(ctx, ctx->d_w_from, from_xyz, (size_t)V * 3)) return 1;
+    if (upload(ctx, ctx->d_w_to, to_xyz, (size_t)V * 3)) return 1;
+    if (upload(ctx, ctx->d_w_tris, tris, (size_t)F * 3)) return 1;
+    if (upload(ctx, ctx->d_w_pts, pts, (size_t)M * 3)) return 1;
+    CK(ctx->d_w_out.ensure((size_t)M * (24 + 24 + 4)));
+    WarpArgs a;
+    a.M = M; a.V = V; a.F = F;
+    a.pts = ctx->d_w_pts.as<double>(); a.from = ctx->d_w_from.as<double>(); a.to = ctx->d_w_to.as<double>(); a.tris = ctx->d_w_tris.as<int>();
+    a.grid.G = G; a.grid.inv_h = 1.0 / h; a.grid.cell_start = ctx->d_w_start.as<int>(); a.grid.items = ctx->d_w_items.as<int>();
+    a.radius = radius;
+    a.out = ctx->d_w_out.as<double>();
+    a.w_out = w_out ? a.out + (size_t)3 * M : nullptr;
+    a.tri_out = tri_out ? reinterpret_cast<int*>(a.out + (size_t)6 * M) : nullptr;
+    {
+        Timer tm(ctx, "mesh_interpolate");
+        k_mesh_interpolate<<<(M + 127) / 128, 128, 0, ctx->stream>>>(a);
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, a.out, (size_t)M * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (w_out) CK(cudaMemcpyAsync(w_out, a.w_out, (size_t)M * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (tri_out) CK(cudaMemcpyAsync(tri_out, a.tri_out, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -64,6 +64,25 @@ def icosphere(level, radius=100.0, _lib_override=None):
     return xyz, tris
 
 
+def mesh_interpolate(up, init_xyz, tris, final_xyz, _lib_override=None):
+    """newresampler::barycentric_mesh_interpolation(SPH_up, SPH_low_init, SPH_low_final) — GPU; returns the moved points."""
+    L = _lib_override or lib()
+    up = np.array(up, dtype=np.float64, order="C", copy=True)
+    init_xyz, pi = _d(init_xyz); tris, pt = _i(tris); final_xyz, pf = _d(final_xyz)
+    if L.msmhost_mesh_interpolate(up.ctypes.data_as(c_dp), len(up), pi, len(init_xyz), pt, len(tris), pf) != 0:
+        raise HostError(L.msmhost_last_error().decode())
+    return up
+
+
+def unfold(xyz, tris, _lib_override=None):
+    """newmeshreg::unfold (src/reg_tools.cpp:134-181), host side."""
+    L = _lib_override or lib()
+    xyz = np.array(xyz, dtype=np.float64, order="C", copy=True); tris, pt = _i(tris)
+    if L.msmhost_unfold(xyz.ctypes.data_as(c_dp), len(xyz), pt, len(tris)) != 0:
+        raise HostError(L.msmhost_last_error().decode())
+    return xyz
+
+
 class Model:
     """NonLinearSRegDiscreteModel (+ its GPU-backed cost function) behind the harness."""
 

@@ -211,9 +211,85 @@ int msmhost_model_triplet_moves(void* h, const int* labeling, int alpha, double*
     return guard([&] { b->model->getNonLinearCostFunction()->computeTripletMoves(labeling, alpha, out); });
 }
 
+// ---- mesh warp -----------------------------------------------------------------------------------
+// barycentric_mesh_interpolation(SPH_up, SPH_low_init, SPH_low_final) on raw arrays; `up` is updated in place
+int msmhost_mesh_interpolate(double* up, int m, const double* init_xyz, int nv, const int* tris, int nf, const double* final_xyz) {
+    return guard([&] {
+        newresampler::Mesh U, A, B;
+        std::vector<int> none;
+        U.set(up, m, none.data(), 0);
+        A = mesh_from(init_xyz, nv, tris, nf);
+        B = mesh_from(final_xyz, nv, tris, nf);
+        newresampler::barycentric_mesh_interpolation(U, A, B);
+        auto c = U.coords();
+        std::memcpy(up, c.data(), c.size() * sizeof(double));
+    });
+}
+int msmhost_unfold(double* xyz, int nv, const int* tris, int nf) {
+    return guard([&] {
+        newresampler::Mesh M = mesh_from(xyz, nv, tris, nf);
+        unfold(M, false);
+        auto c = M.coords();
+        std::memcpy(xyz, c.data(), c.size() * sizeof(double));
+    });
+}
+
 #ifdef WITH_REF_OPTIM
 // ---- unmodified reference optimisers ------------------------------------------------------------------------------
 int ref_available() { return 1; }
+// Mesh_registration::run_discrete_opt (src/mesh_registration.cpp:316-397) restated on the mirror classes with the
+// reference's own optimisers: per outer iteration reset_meshspace -> setupCostFunction -> FastPD | HOCR -> convergence
+// test -> applyLabeling -> warp the source by the control-grid update -> unfold both.  `source` (the data mesh, same
+// topology as the target template) is updated in place; labelings/energies/seconds are per iteration (size iters).
+// Returns the number of iterations run, or -1 on error.
+int ref_run_discrete_opt(void* h, int iters, int threads, double* source_xyz, int* labelings, double* energies, double* seconds_cost,
+                         double* seconds_opt, double* seconds_warp) {
+    auto* b = (ModelBox*)h;
+    int done = 0;
+    const int st = guard([&] {
+        const std::string dopt = boost::get<std::string>(b->params.find("dOPT")->second);
+        newresampler::Mesh source = b->source;
+        for (int i = 0; i < source.nvertices(); i++) source.set_coord(i, newresampler::Point(source_xyz[3 * i], source_xyz[3 * i + 1], source_xyz[3 * i + 2]));
+        double energy = 0.0, newenergy = 0.0;
+        for (int iter = 1; iter <= iters; iter++) {
+            double t0 = omp_get_wtime();
+            NEWMAT::Matrix CombinedWeight;                       // :330-334 (no cost-function weighting supplied)
+            CombinedWeight.resize(1, source.nvertices());
+            CombinedWeight = 1;
+            b->model->setupCostFunctionWeighting(CombinedWeight);
+            b->model->reset_meshspace(source);
+            b->model->setupCostFunction();
+            double t1 = omp_get_wtime();
+            if (dopt == "FastPD") {
+                b->model->computeUnaryCosts();
+                b->model->computePairwiseCosts();
+                FPD::FastPD opt(b->model, 100);
+                newenergy = opt.run();
+                opt.getLabeling(b->model->getLabeling());
+            } else if (dopt == "HOCR") {
+                newenergy = Fusion::optimize(b->model, false, threads);
+            } else throw MeshregException("Unrecognized optimiser");
+            double t2 = omp_get_wtime();
+            std::memcpy(labelings + (size_t)(iter - 1) * b->model->getNumNodes(), b->model->getLabeling(), sizeof(int) * b->model->getNumNodes());
+            energies[iter - 1] = newenergy;
+            seconds_cost[iter - 1] = t1 - t0; seconds_opt[iter - 1] = t2 - t1; seconds_warp[iter - 1] = 0;
+            done = iter;
+            if (iter > 1 && ((iter - 1) % 2 == 0) && (energy - newenergy < 0.001)) break;   // :370-377
+            newresampler::Mesh previous_controlgrid = b->model->get_CPgrid();
+            b->model->applyLabeling();
+            newresampler::Mesh transformed_controlgrid = b->model->get_CPgrid();
+            newresampler::barycentric_mesh_interpolation(source, previous_controlgrid, transformed_controlgrid, threads);
+            unfold(transformed_controlgrid, false);
+            b->model->reset_CPgrid(transformed_controlgrid);
+            unfold(source, false);
+            energy = newenergy;
+            seconds_warp[iter - 1] = omp_get_wtime() - t2;
+        }
+        auto c = source.coords();
+        std::memcpy(source_xyz, c.data(), c.size() * sizeof(double));
+    });
+    return st == 0 ? done : -1;
+}
 // src/mesh_registration.cpp:346-352
 int ref_fastpd_model(void* h, double* energy) {
     auto* b = (ModelBox*)h;

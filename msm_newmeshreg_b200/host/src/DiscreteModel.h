@@ -7,6 +7,7 @@
 #include <omp.h>
 
 #include "DiscreteCostFunction.h"
+#include "mesh_warp.h"
 
 namespace newmeshreg {
 
@@ -219,6 +220,10 @@ public:
     void setupCostFunctionWeighting(const NEWMAT::Matrix& Weight) { costfct->set_dataaffintyweighting(Weight); }
     virtual void reset_meshspace(const newresampler::Mesh& source, int num = 0) { m_SOURCE = source; costfct->reset_source(source); }
     virtual void reset_CPgrid(const newresampler::Mesh& grid, int num = 0) { m_CPgrid = grid; }
+    virtual void warp_CPgrid(newresampler::Mesh& START, newresampler::Mesh& END, int num = 0) {  // src/DiscreteModel.h:122-125
+        newresampler::barycentric_mesh_interpolation(m_CPgrid, START, END, _nthreads);
+        unfold(m_CPgrid, m_verbosity);
+    }
     void set_debug() { m_debug = true; costfct->debug(); }
     void report() override { if (costfct) costfct->report(); }
     newresampler::Mesh get_TARGET() { return m_TARGET; }

@@ -75,6 +75,17 @@ inline NEWMAT::Matrix estimate_rotation_matrix(const Point& p1, const Point& p2)
     R(1, 1) = R(2, 2) = R(3, 3) = 1.0;
     if (std::fabs(theta) < 1e-8) return R;
     Point k = a * b;
+    if (k.norm() < 1e-12 && c < 0) {
+        // antiparallel (the antipode of the label-grid centre is a control point of every regular icosphere): rotation by
+        // pi about a x e, e = coordinate axis of a's smallest component — same convention as the device (locate.cuh)
+        const double ax = std::fabs(a.X), ay = std::fabs(a.Y), az = std::fabs(a.Z);
+        Point u = a * ((ax <= ay && ax <= az) ? Point(1, 0, 0) : ((ay <= az) ? Point(0, 1, 0) : Point(0, 0, 1)));
+        u.normalize();
+        const double uu[3] = {u.X, u.Y, u.Z};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) R(i + 1, j + 1) = 2.0 * uu[i] * uu[j] - (i == j ? 1.0 : 0.0);
+        return R;
+    }
     k.normalize();
     const double s = std::sin(theta), oc = 1.0 - std::cos(theta);
     const double u[3][3] = {{0, -k.Z, k.Y}, {k.Z, 0, -k.X}, {-k.Y, k.X, 0}};

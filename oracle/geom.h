@@ -97,6 +97,21 @@ inline Mat3 estimate_rotation_matrix(const Pt& p1, const Pt& p2) {
     Mat3 I;
     if (std::fabs(theta) < 1e-8) return I;
     Pt k = ci * index;
+    if (k.norm() < 1e-12 && c < 0) {
+        // Antiparallel directions: the minimal rotation is by pi about ANY axis perpendicular to a; the published formula
+        // degenerates (axis = normalised zero vector).  Every regular icosphere contains the antipode of the label-grid
+        // centre, so this input does occur (src/DiscreteModel.cpp:284-294).  Convention fixed here (and in the product):
+        // axis = a x e, e = the coordinate axis along which a has its smallest component.
+        const double ax = std::fabs(ci.X), ay = std::fabs(ci.Y), az = std::fabs(ci.Z);
+        Pt e = (ax <= ay && ax <= az) ? Pt(1, 0, 0) : ((ay <= az) ? Pt(0, 1, 0) : Pt(0, 0, 1));
+        Pt u = ci * e;
+        u.normalize();
+        Mat3 R;  // I + 2 (u u^T - I)
+        const double uu[3] = {u.X, u.Y, u.Z};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) R.m[i][j] = 2.0 * uu[i] * uu[j] - (i == j ? 1.0 : 0.0);
+        return R;
+    }
     k.normalize();
     Mat3 u = Mat3::zero();
     u.m[0][1] = -k.Z; u.m[0][2] = k.Y;

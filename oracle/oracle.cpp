@@ -212,6 +212,90 @@ std::vector<Mat3> get_rotations(const Pt& ci, const std::vector<Pt>& cps) {  // 
 }
 
 // =========================================================================================================
+// mesh warp — [EXT] A8 barycentric_mesh_interpolation; unfold and helpers src/reg_tools.cpp:62-181
+// =========================================================================================================
+void barycentric_mesh_interpolation(std::vector<Pt>& up, const Mesh& low_init, const std::vector<Pt>& low_final) {
+    SphereLocator loc(low_init);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < (int)up.size(); i++) {
+        const Pt ci = up[i];
+        const int t = loc.closest_triangle(ci);
+        const auto& f = low_init.F[t];
+        double w[3];
+        barycentric_weights(low_init.V[f[0]], low_init.V[f[1]], low_init.V[f[2]], ci, w);
+        Pt q = low_final[f[0]] * w[0] + low_final[f[1]] * w[1] + low_final[f[2]] * w[2];
+        q.normalize();
+        up[i] = q * RAD;
+    }
+}
+
+static void computeNormal2EdgeOfTriangle(const Pt& v0, const Pt& v1, const Pt& v2, Pt& norm2edge) {  // :62-82
+    Pt s1 = v2 - v0, s2 = v1 - v0;
+    if (s1.norm() > 1e-10) s1.normalize(); else s1 = Pt(0, 0, 0);
+    if (s2.norm() > 1e-10) s2.normalize(); else s2 = Pt(0, 0, 0);
+    Pt norm2triangle = s1 * s2;
+    if (norm2triangle.norm() > 1e-10) norm2triangle.normalize(); else norm2triangle = Pt(0, 0, 0);
+    norm2edge = s2 * norm2triangle;
+    if ((s1 | norm2edge) < 0) norm2edge = norm2edge * -1;
+}
+
+static Pt computeGradientOfBarycentricTriangle(const Pt& v0, const Pt& v1, const Pt& v2) {  // :84-95
+    Pt norm2edge;
+    computeNormal2EdgeOfTriangle(v0, v1, v2, norm2edge);
+    const double base = (v1 - v0).norm();
+    return norm2edge * 0.5 * base;
+}
+
+Pt spatialgradient(int index, const Mesh& M) {  // :97-119
+    Pt grad, ci = M.get_coord(index);
+    for (int j : M.vtri[index]) {
+        const Pt v0 = M.V[M.F[j][0]], v1 = M.V[M.F[j][1]], v2 = M.V[M.F[j][2]];
+        Pt dA;
+        if ((ci - v0).norm() == 0) dA = computeGradientOfBarycentricTriangle(v1, v2, v0);
+        else if ((ci - v1).norm() == 0) dA = computeGradientOfBarycentricTriangle(v2, v0, v1);
+        else dA = computeGradientOfBarycentricTriangle(v0, v1, v2);
+        grad = grad + dA;
+    }
+    return grad;
+}
+
+bool check_for_intersections(int ind, const Mesh& M) {  // :121-132 (get_triangle_from_vertex(ind,0) = first incident face)
+    const Pt N = M.get_triangle(M.vtri[ind][0]).normal();
+    for (int j : M.vtri[ind])
+        if ((N | M.get_triangle(j).normal()) <= 0.5) return true;
+    return false;
+}
+
+int unfold(Mesh& SOURCE) {  // :134-181
+    std::vector<int> folded;
+    std::vector<Pt> grads;
+    int it = 0;
+    while (true) {
+        folded.clear(); grads.clear();
+        for (int i = 0; i < SOURCE.nvertices(); i++)
+            if (check_for_intersections(i, SOURCE)) folded.push_back(i);
+        if (folded.empty()) return it;
+        for (int v : folded) grads.push_back(spatialgradient(v, SOURCE));
+        for (size_t i = 0; i < folded.size(); i++) {
+            double step = 1.0;
+            const Pt ci = SOURCE.get_coord(folded[i]);
+            const Pt grad = grads[i];
+            Pt pp;
+            do {
+                pp = ci - grad * step;
+                pp.normalize();
+                SOURCE.set_coord(folded[i], pp * RAD);
+                step *= 0.5;
+            } while (check_for_intersections(folded[i], SOURCE) && step > 1e-3);
+            SOURCE.set_coord(folded[i], pp * RAD);
+        }
+        it++;
+        if (it == 1000) break;
+    }
+    return it;
+}
+
+// =========================================================================================================
 // cost function — src/DiscreteCostFunction.cpp
 // =========================================================================================================
 void CostFunction::set_meshes(const Mesh& target, const Mesh& source, const Mesh& grid) {  // .h:166-168

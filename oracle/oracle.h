@@ -59,6 +59,13 @@ std::vector<int> estimate_triplets(const Mesh& CP);                             
 std::vector<int> estimate_pairs(const Mesh& CP);                                         // :245-265
 std::vector<Mat3> get_rotations(const Pt& centre, const std::vector<Pt>& cps);           // :284-294
 
+// ---- mesh warp: [EXT] A8 barycentric_mesh_interpolation + src/reg_tools.cpp:62-181 unfold ----
+// up[i] <- normalise( sum_j w_j * low_final[n_j] ) * RAD with (n_j, w_j) = closest triangle of low_init + barycentric weights
+void barycentric_mesh_interpolation(std::vector<Pt>& up, const Mesh& low_init, const std::vector<Pt>& low_final);
+bool check_for_intersections(int ind, const Mesh& M);   // :121-132
+Pt spatialgradient(int index, const Mesh& M);           // :97-119
+int unfold(Mesh& SOURCE);                               // :134-181, returns the number of sweeps performed
+
 // ---- cost function: NonLinearSRegDiscreteCostFunction + Univariate/Multivariate variants ----
 class CostFunction {
 public:

@@ -95,6 +95,28 @@ void orc_locate(const double* xyz, int nv, const int* tris, int nf, const double
     }
 }
 
+// ---------------- mesh warp ----------------
+void orc_mesh_interpolate(const double* pts, int m, const double* from_xyz, int nv, const int* tris, int nf, const double* to_xyz, double* out) {
+    Mesh M = mesh_from(from_xyz, nv, tris, nf);
+    std::vector<Pt> up(m), fin(nv);
+    for (int i = 0; i < m; i++) up[i] = Pt(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    for (int i = 0; i < nv; i++) fin[i] = Pt(to_xyz[3 * i], to_xyz[3 * i + 1], to_xyz[3 * i + 2]);
+    barycentric_mesh_interpolation(up, M, fin);
+    for (int i = 0; i < m; i++) { out[3 * i] = up[i].X; out[3 * i + 1] = up[i].Y; out[3 * i + 2] = up[i].Z; }
+}
+int orc_unfold(double* xyz, int nv, const int* tris, int nf) {
+    Mesh M = mesh_from(xyz, nv, tris, nf);
+    int it = unfold(M);
+    for (int i = 0; i < nv; i++) { xyz[3 * i] = M.V[i].X; xyz[3 * i + 1] = M.V[i].Y; xyz[3 * i + 2] = M.V[i].Z; }
+    return it;
+}
+int orc_count_folded(const double* xyz, int nv, const int* tris, int nf) {
+    Mesh M = mesh_from(xyz, nv, tris, nf);
+    int n = 0;
+    for (int i = 0; i < nv; i++) n += check_for_intersections(i, M) ? 1 : 0;
+    return n;
+}
+
 // ---------------- cost function object ----------------
 void* orc_cf_create() { return new CostFunction(); }
 void orc_cf_destroy(void* h) { delete (CostFunction*)h; }

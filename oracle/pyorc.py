@@ -126,6 +126,26 @@ def locate(xyz, tris, pts, brute=False, orthogonal=False):
     return tri, w
 
 
+def mesh_interpolate(pts, from_xyz, tris, to_xyz):
+    """[EXT] barycentric_mesh_interpolation(SPH_up, SPH_low_init, SPH_low_final) restated (src/mesh_registration.cpp:390)."""
+    pts, pp = _d(pts); from_xyz, pf = _d(from_xyz); tris, pt = _i(tris); to_xyz, po = _d(to_xyz)
+    out = np.empty((len(pts), 3))
+    lib().orc_mesh_interpolate(pp, len(pts), pf, len(from_xyz), pt, len(tris), po, out.ctypes.data_as(c_dp))
+    return out
+
+
+def unfold(xyz, tris):
+    """unfold (src/reg_tools.cpp:134-181): returns (new coordinates, sweeps performed)."""
+    xyz = np.array(xyz, dtype=np.float64, order="C", copy=True); tris, pt = _i(tris)
+    it = lib().orc_unfold(xyz.ctypes.data_as(c_dp), len(xyz), pt, len(tris))
+    return xyz, it
+
+
+def count_folded(xyz, tris):
+    xyz, px = _d(xyz); tris, pt = _i(tris)
+    return lib().orc_count_folded(px, len(xyz), pt, len(tris))
+
+
 class CostFunction:
     """Mirror of NonLinearSRegDiscreteCostFunction (+Uni/Multi variants), src/DiscreteCostFunction.{h,cpp}."""
 

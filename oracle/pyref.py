@@ -61,6 +61,20 @@ def fusion_model(m, threads=1):
     return m.labeling(), e.value
 
 
+def run_discrete_opt(m, source_xyz, iters, threads=1):
+    """Mesh_registration::run_discrete_opt (src/mesh_registration.cpp:316-397) on the GPU-backed model `m` with the
+    reference's own optimiser (FastPD or HOCR per the model's dOPT).  Returns (warped source, labelings[it][N],
+    energies[it], timings dict of per-iteration seconds)."""
+    src = np.array(source_xyz, dtype=np.float64, order="C", copy=True)
+    labs = np.zeros((iters, m.N), np.int32)
+    en = np.zeros(iters); tc = np.zeros(iters); to = np.zeros(iters); tw = np.zeros(iters)
+    n = lib().ref_run_discrete_opt(m.h, iters, threads, src.ctypes.data_as(c_dp), labs.ctypes.data_as(c_ip), en.ctypes.data_as(c_dp),
+                                   tc.ctypes.data_as(c_dp), to.ctypes.data_as(c_dp), tw.ctypes.data_as(c_dp))
+    if n < 0:
+        raise RuntimeError(lib().msmhost_last_error().decode())
+    return src, labs[:n], en[:n], {"cost": tc[:n], "optimiser": to[:n], "warp": tw[:n]}
+
+
 def fastpd_tables(unary, pairs, pairtab):
     """FPD::FastPD (include/FastPD/FastPD.h) on explicit tables: unary [L][N], pairtab [P][L][L] (reference layout)."""
     L, N = unary.shape

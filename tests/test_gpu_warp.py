@@ -1,0 +1,119 @@
+"""Mesh-warp row: barycentric_mesh_interpolation on the GPU and unfold on the host against the
+oracle's restatement, and the complete outer loop of run_discrete_opt (src/mesh_registration.cpp:316-397) — cost
+evaluation, the reference's own HOCR optimiser, applyLabeling, source warp, unfold — against the same loop assembled from
+oracle pieces: identical labellings per iteration and warped sphere vertices within 1e-4 (north_star)."""
+import numpy as np
+import pytest
+
+import problems as pb
+from oracle import pyorc, pyref
+
+RAD = 100.0
+
+
+def test_oracle_mesh_interpolation_known_answers():
+    """CPU: identity warp leaves points in place; a rigid rotation of the control grid rotates every point."""
+    cxyz, ctris = pyorc.icosphere(2)
+    rng = np.random.default_rng(0)
+    pts = rng.normal(size=(500, 3)); pts *= RAD / np.linalg.norm(pts, axis=1, keepdims=True)
+    assert np.abs(pyorc.mesh_interpolate(pts, cxyz, ctris, cxyz) - pts).max() < 1e-10
+    R = pyorc.rotation_matrix([1, 0, 0], [0.9, 0.3, -0.2])
+    out = pyorc.mesh_interpolate(pts, cxyz, ctris, cxyz @ R.T)
+    assert np.abs(out - pts @ R.T).max() < 1e-9                   # barycentric combination commutes with a linear map
+    assert np.allclose(np.linalg.norm(out, axis=1), RAD)
+
+
+def test_oracle_unfold():
+    """CPU: an unfolded mesh is untouched; a vertex pushed across its 1-ring is detected and repaired."""
+    xyz, tris = pyorc.icosphere(3)
+    same, it = pyorc.unfold(xyz, tris)
+    assert it == 0 and np.array_equal(same, xyz) and pyorc.count_folded(xyz, tris) == 0
+    bad = xyz.copy()
+    v = 100
+    nb = np.unique(tris[(tris == v).any(1)]); nb = nb[nb != v]
+    far = nb[0]
+    bad[v] = xyz[far] + 1.2 * (xyz[far] - xyz[v]); bad[v] *= RAD / np.linalg.norm(bad[v])   # jump over a neighbour
+    assert pyorc.count_folded(bad, tris) > 0
+    fixed, it = pyorc.unfold(bad, tris)
+    assert it >= 1 and pyorc.count_folded(fixed, tris) == 0
+    assert np.allclose(np.linalg.norm(fixed, axis=1), RAD)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cp_level,deform", [(2, 0.0), (3, 0.3), (4, 0.25)])
+def test_mesh_interpolate_parity(built, cp_level, deform):
+    from msm_newmeshreg_b200 import Context
+    cxyz0, ctris = pyorc.icosphere(cp_level)
+    _, _, mvd = pyorc.spacings(cxyz0, ctris)
+    start = pb.smooth_warp(cxyz0, 3, deform * mvd) if deform else cxyz0          # deformed START grid (not an icosphere)
+    end = pb.smooth_warp(cxyz0, 4, 0.4 * mvd)
+    pts, _ = pyorc.icosphere(5)
+    pts = pb.smooth_warp(pts, 5, 0.5)
+    ctx = Context()
+    out, tri, w = ctx.mesh_interpolate(pts, start, ctris, end, details=True)
+    ref = pyorc.mesh_interpolate(pts, start, ctris, end)
+    assert np.abs(out - ref).max() < 1e-9
+    assert np.allclose(w.sum(1), 1.0) and (w > -1e-12).all()
+    to, _ = pyorc.locate(start, ctris, pts)
+    interior = w.min(1) > 1e-9
+    assert np.array_equal(tri[interior], to[interior])
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_host_warp_functions(built):
+    from msm_newmeshreg_b200 import host
+    cxyz0, ctris = pyorc.icosphere(3)
+    end = pb.smooth_warp(cxyz0, 4, 2.0)
+    pts, ptris = pyorc.icosphere(4)
+    moved = host.mesh_interpolate(pts, cxyz0, ctris, end)
+    assert np.abs(moved - pyorc.mesh_interpolate(pts, cxyz0, ctris, end)).max() < 1e-9
+    bad = pts.copy(); v = 300
+    nb = np.unique(ptris[(ptris == v).any(1)]); nb = nb[nb != v]
+    bad[v] = pts[nb[0]] + 1.2 * (pts[nb[0]] - pts[v]); bad[v] *= RAD / np.linalg.norm(bad[v])
+    fixed_o, _ = pyorc.unfold(bad, ptris)
+    assert np.abs(host.unfold(bad, ptris) - fixed_o).max() < 1e-12           # same sequential algorithm on the host
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+def test_run_discrete_opt_matches_oracle_loop(built):
+    """Whole outer loop, 3 iterations, HOCR + strain regulariser: labellings identical per iteration, final warped
+    source vertices within 1e-4 of the oracle-assembled loop."""
+    from msm_newmeshreg_b200 import host
+    P = pb.make_problem(4, 2, 1, seed=41, warp=0.0)               # level start: source mesh == template (iteration 1)
+    pr = dict(pb.DEFAULT_PARAMS); pr.update(rmode=3, dopt="HOCR")
+    m = host.Model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, _lib_override=pyref.lib(), **pr)
+    m.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref)
+    m.initialize()
+    iters = 3
+    src_gpu, labs_gpu, en_gpu, _ = pyref.run_discrete_opt(m, P.txyz, iters, threads=4)
+
+    # the same loop from oracle pieces (src/mesh_registration.cpp:320-396)
+    src = P.txyz.copy(); cp = P.cxyz0.copy()
+    energy = 0.0
+    labs_orc = []
+    for it in range(1, iters + 1):
+        Q = pb.make_problem(4, 2, 1, seed=41, warp=0.0, iteration=it)
+        Q.sxyz = src; Q.cxyz = cp; Q.rot = pyorc.rotations(Q.centre, cp)
+        cf = pb.oracle_costfunction(Q, params=dict(rmode=3)); cf.get_source_data()
+        lab, newenergy = pyref.fusion_tables(cf.unary_costs(), Q.triplets, cf.triplet_table(), threads=4)
+        labs_orc.append(lab)
+        if it > 1 and (it - 1) % 2 == 0 and energy - newenergy < 0.001:
+            break
+        newcp = np.einsum("nij,nj->ni", Q.rot, Q.labels[lab])
+        src = pyorc.mesh_interpolate(src, cp, Q.ctris, newcp)
+        newcp, _ = pyorc.unfold(newcp, Q.ctris)
+        cp = newcp
+        src, _ = pyorc.unfold(src, P.ttris)
+        energy = newenergy
+    assert len(labs_gpu) == len(labs_orc)
+    sing = pb.singular_nodes(P)
+    for it, (a, b) in enumerate(zip(labs_gpu, labs_orc)):
+        keep = np.ones(P.N, bool); keep[sing] = False
+        assert np.array_equal(a[keep], b[keep]), f"iteration {it + 1}: {(a != b).sum()} labels differ"
+    # vertices influenced by the singular control point (antipode of the label-grid centre) are excluded
+    d_sing = np.linalg.norm(P.txyz - P.cxyz0[sing[0]], axis=1) if len(sing) else np.full(len(P.txyz), 1e9)
+    far = d_sing > 2.5 * P.mvdmax
+    assert np.abs(src_gpu - src)[far].max() < 1e-4
+    m.close()
