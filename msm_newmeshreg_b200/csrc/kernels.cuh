@@ -516,11 +516,42 @@ __global__ void __launch_bounds__(256) k_triplet_table(TripArgs a, int t0, float
         sd[i] = a.disp[(size_t)id[v] * L * 3 + r];
     }
     __syncthreads();
+    const bool fast = (a.p.group || (a.p.rmode == 3 && a.p.k_exp == 2.0));   // strain energy with k = 2: no sqrt / pow
+    const double inv0 = 1.0 / g.det0;
     for (int ab = threadIdx.x; ab < L2; ab += blockDim.x) {
         const int la = ab / L, lb = ab - la * L;
         const double* d0 = sd + 3 * la;
         const double* d1 = sd + 3 * L + 3 * lb;
-        for (int lc = 0; lc < L; lc++) sres[ab * L + lc] = (float)trip_cost(a.p, g, d0, d1, sd + 6 * L + 3 * lc);
+        if (!fast) {
+            for (int lc = 0; lc < L; lc++) sres[ab * L + lc] = (float)trip_cost(a.p, g, d0, d1, sd + 6 * L + 3 * lc);
+            continue;
+        }
+        // everything that depends on (la, lb) only is hoisted out of the lc loop
+        const double e1[3] = {d1[0] - d0[0], d1[1] - d0[1], d1[2] - d0[2]};
+        const double g11 = dot3(e1, e1);
+        double c[3];
+        cross3(g.n, e1, c);                       // (e1 x e2).n = e2.(n x e1)
+        const double t11 = g11 * g.G22 * inv0, t12 = -2.0 * g.G12 * inv0, t22 = g.G11 * inv0;
+        for (int lc = 0; lc < L; lc++) {
+            const double* d2 = sd + 6 * L + 3 * lc;
+            const double e2[3] = {d2[0] - d0[0], d2[1] - d0[1], d2[2] - d0[2]};
+            const double g12 = dot3(e1, e2), g22 = dot3(e2, e2);
+            const bool fold = dot3(e2, c) < 0.0;
+            const double trC = t11 + t12 * g12 + t22 * g22;
+            const double I3 = (g11 * g22 - g12 * g12) * inv0;
+            const double r = 1.0 / I3;
+            const double i1s2 = trC * trC * r;
+            double W = 0.5 * (a.p.mu * fmax(i1s2 - 4.0, 0.0) + a.p.kappa * (I3 + r - 2.0));
+            double res;
+            if (a.p.group) res = fold ? 1e7 : a.p.lambda * ((a.p.rexp == 2.0) ? W * W : pow(W, a.p.rexp));
+            else {
+                double weight = 1.0;
+                if (fold) { W = 1.0; weight += 1e6; }
+                if (fabs(W) < 1e-8) W = 0.0;
+                res = weight * a.p.lambda * ((a.p.rexp == 2.0) ? W * W : pow(W, a.p.rexp));
+            }
+            sres[ab * L + lc] = (float)res;
+        }
     }
     __syncthreads();
     float* o = out + (size_t)blockIdx.x * L3;

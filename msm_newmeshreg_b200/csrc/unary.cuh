@@ -57,31 +57,46 @@ struct UnarySetupArgs {
     float* pcx; float* pcy; float* pcz; // [total] corner coordinates of the unrotated samples
 };
 
-__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a) {
+// one THREAD per control point: hint face, its dual basis applied to CP_k, and the reference target value — the only
+// serial fp64 descents of the set-up, taken out of k_unary_setup so that no CTA waits on a single thread
+__global__ void __launch_bounds__(128) k_cp_hint(UnarySetupArgs a, int Ns, double* __restrict__ x0_out /*[Ns][3]*/) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= Ns) return;
+    const int k = a.k_begin + row;
+    const double ox = a.cp[3 * k], oy = a.cp[3 * k + 1], oz = a.cp[3 * k + 2];
+    int base, n; double al, be, ga;
+    descend_d(a.ico, a.hint.h, ox, oy, oz, base, n, al, be, ga);
+    const int f = base * a.hint.nf_per_base + (n - a.hint.node_off);
+    a.hint_face[row] = f;
+    const double* Ag = a.hint.hdual + (size_t)f * 9;
+    x0_out[3 * row + 0] = Ag[0] * ox + Ag[1] * oy + Ag[2] * oz;
+    x0_out[3 * row + 1] = Ag[3] * ox + Ag[4] * oy + Ag[5] * oz;
+    x0_out[3 * row + 2] = Ag[6] * ox + Ag[7] * oy + Ag[8] * oz;
+    float tr = 0.f;
+    if (a.face_feat) {  // continue the same descent down to the leaf
+        for (int l = a.hint.h; l < a.ico.depth; l++) {
+            const double4 nn = a.ico.ntab_d[n];
+            const double s = al + be + ga;
+            const double sa = (al + al) - s, sb = (be + be) - s, sc = (ga + ga) - s;
+            int child; double x, y, z;
+            if (sa > 0.0) { child = 0; x = sa; y = be * nn.x; z = ga * nn.z; }
+            else if (sb > 0.0) { child = 1; x = al * nn.x; y = sb; z = ga * nn.y; }
+            else if (sc > 0.0) { child = 2; x = al * nn.z; y = be * nn.y; z = sc; }
+            else { child = 3; x = -sa * nn.y; y = -sb * nn.z; z = -sc * nn.x; }
+            al = x; be = y; ga = z;
+            n = 4 * n + 1 + child;
+        }
+        tr = reinterpret_cast<const float4*>(a.face_feat)[base * a.ico.nleaf_per_base + (n - a.ico.leaf_off)].x;
+    }
+    a.tref[row] = tr;
+}
+
+__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, const double* __restrict__ x0_in) {
     const int row = blockIdx.x, k = a.k_begin + row, tid = threadIdx.x;
     __shared__ double A[9], x0[3];
     const double ox = a.cp[3 * k], oy = a.cp[3 * k + 1], oz = a.cp[3 * k + 2];
-    if (tid == 0) {
-        int base, n; double al, be, ga;
-        descend_d(a.ico, a.hint.h, ox, oy, oz, base, n, al, be, ga);
-        const int f = base * a.hint.nf_per_base + (n - a.hint.node_off);
-        a.hint_face[row] = f;
-        const double* Ag = a.hint.hdual + (size_t)f * 9;
-#pragma unroll
-        for (int i = 0; i < 9; i++) A[i] = Ag[i];
-        x0[0] = Ag[0] * ox + Ag[1] * oy + Ag[2] * oz;
-        x0[1] = Ag[3] * ox + Ag[4] * oy + Ag[5] * oz;
-        x0[2] = Ag[6] * ox + Ag[7] * oy + Ag[8] * oz;
-    }
-    if (tid == 32) {
-        float tr = 0.f;
-        if (a.face_feat) {
-            int base, n; double al, be, ga;
-            descend_d(a.ico, a.ico.depth, ox, oy, oz, base, n, al, be, ga);
-            tr = reinterpret_cast<const float4*>(a.face_feat)[base * a.ico.nleaf_per_base + (n - a.ico.leaf_off)].x;
-        }
-        a.tref[row] = tr;
-    }
+    if (tid < 9) A[tid] = a.hint.hdual[(size_t)a.hint_face[row] * 9 + tid];
+    else if (tid < 12) x0[tid - 9] = x0_in[3 * row + tid - 9];
     __syncthreads();
     for (int s = a.off[row] + tid; s < a.off[row + 1]; s += 128) {
         const double x = a.px[s], y = a.py[s], z = a.pz[s];

@@ -250,6 +250,59 @@ def test_group_triplets(built):
     ctx.close()
 
 
+def test_group_pairwise_patch_correlation(built):
+    """DiscreteGroupCostFunction::computePairwiseCost (src/DiscreteGroupCostFunction.cpp:32-54): correlation over the
+    intersection of two (template vertex -> value) patch maps, incl. empty and single-element intersections."""
+    from msm_newmeshreg_b200 import Context
+    rng = np.random.default_rng(5)
+    S, N, L, V = 3, 12, 5, 400
+    nmaps = S * N * L
+    off = [0]; keys = []; vals = []
+    for m in range(nmaps):
+        n = int(rng.integers(0, 60))
+        k = np.sort(rng.choice(V // (1 if m % 7 else 8), size=min(n, V // 8), replace=False))   # some maps sparse / disjoint
+        keys.append(k); vals.append(rng.normal(size=len(k)) + (5.0 if m % 3 == 0 else 0.0))
+        off.append(off[-1] + len(k))
+    keys = np.concatenate(keys).astype(np.int32); vals = np.concatenate(vals)
+    pairs = np.array([[a * N + v, b * N + int(rng.integers(0, N))] for a in range(S) for v in range(N) for b in range(a + 1, S)], np.int32)
+    cps = np.tile(pyorc.icosphere(0)[0], (S, 1))                      # 12 control points per subject (geometry unused here)
+    ctx = Context()
+    ctx.set_params(group=True, rmode=3)
+    ctx.set_cpgrid(cps, np.zeros((0, 3), np.int32), np.ones(S * N), cps)
+    ctx.set_group(S, N, 20)
+    labels = np.tile(cps[0], (L, 1)) + rng.normal(size=(L, 3)) * 0.01
+    ctx.set_labels(labels, labels[0])
+    ctx.set_pairs(pairs)
+    ctx.set_group_patches(off, keys, vals)
+    gc = pyorc.GroupCost()
+    gc.set(1.0, 2.0, 0.4, 1.6, cps.reshape(S, N, 3), pyorc.icosphere(0)[1], cps[:N], labels, np.tile(np.eye(3), (S * N, 1, 1)),
+           np.zeros((S * 20, 3), np.int32))
+    gc.set_patches(off, keys, vals, pairs)
+    q = np.stack([rng.integers(0, len(pairs), 3000), rng.integers(0, L, 3000), rng.integers(0, L, 3000)], 1).astype(np.int32)
+    g, o = ctx.group_pair_costs(q), gc.pair_costs(q)
+    assert np.abs(g - o).max() < 1e-12
+    assert (o == 0.5).any()                                           # empty / degenerate intersections give rho = 0
+    lab = rng.integers(0, L, S * N).astype(np.int32)
+    mv = ctx.group_pair_moves(lab, 2)
+    qm = np.array([[p, 2 if c & 2 else lab[pairs[p, 0]], 2 if c & 1 else lab[pairs[p, 1]]] for p in range(len(pairs)) for c in range(4)], np.int32)
+    assert np.abs(mv.ravel() - gc.pair_costs(qm)).max() < 1e-12      # include/Fusion/Fusion.h:169-172 order
+    ctx.close()
+
+
+def test_antipodal_control_point_is_well_defined(built):
+    """The control point antipodal to the label-grid centre: rotation by pi about the agreed axis on both sides."""
+    P = pb.make_problem(4, 2, 1, seed=14, warp=0.3)
+    sing = pb.singular_nodes(P)
+    assert len(sing) == 1
+    ctx = pb.gpu_context(P); ctx.build_patches()
+    cf = pb.oracle_costfunction(P); cf.get_source_data()
+    _check(ctx.unary_table()[:, sing], cf.unary_costs()[:, sing], UFLOOR, "unary at the antipodal CP")
+    ts = np.nonzero((P.triplets == sing[0]).any(1))[0]
+    q = np.array([[t, a, b, c] for t in ts for a in (0, 3, 7) for b in (0, 5) for c in (0, 2, 11)], np.int32)
+    _check(ctx.triplet_costs(q), cf.triplet_costs(q), 1e-3 * pb.DEFAULT_PARAMS["lam"], "triplets at the antipodal CP", tol=1e-9)
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ pairwise
 def test_pair_table_parity(built):
     P = pb.make_problem(4, 2, 1, seed=12, warp=0.3, deform_cp=0.2)
