@@ -246,8 +246,7 @@ int ensure_face_feat(msm_ctx* ctx) {
     const int want = ctx->multivariate ? (ctx->Ct + 3) / 4 : 0;
     if (!ctx->multivariate && ctx->Ct != 1) FAIL("univariate cost function needs C == 1");
     if (ctx->face_feat_cq == want) return 0;
-    if (want > 4) FAIL("multivariate cost function supports at most 16 channels in this build");
-    const int Cp = want == 0 ? 1 : 4 * want;
+    const int Cp = want == 0 ? 1 : 4 * want;   // any channel count: > 16 channels run the generic kernel variant
     const size_t per_face = want == 0 ? 4 : (size_t)3 * Cp;
     CK(ctx->d_face_feat.ensure((size_t)ctx->Ft * per_face * sizeof(float)));
     k_face_pack<<<(ctx->Ft + 255) / 256, 256, 0, ctx->stream>>>(ctx->Ft, ctx->Ct, Cp, ctx->Vt, want == 0 ? 1 : 0, ctx->d_leaf_vid.as<int>(),
@@ -754,8 +753,9 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
     if (ensure_hint_level(ctx)) return 1;
     const int Ns = ctx->k_end - ctx->k_begin;
     if (Ns == 0) return 0;
-    const int CQ = ctx->face_feat_cq;
-    const int Cp = CQ == 0 ? 1 : 4 * CQ;
+    const int cq_actual = ctx->face_feat_cq;                 // channel quads of the face-packed layout
+    const int CQ = cq_actual <= 4 ? cq_actual : 5;           // kernel variant (5 = generic, features read from global)
+    const int Cp = CQ == 0 ? 1 : (CQ <= 4 ? 4 * CQ : 0);     // channels staged in shared memory
     const int L = ctx->L, Pmax = std::max(ctx->maxP, 1);
     // label groups: fit shared memory (<= ~56 KB so several CTAs share an SM) and expose >= 4 CTAs per SM
     auto smem_for = [&](int Lg) { return (size_t)4 * ((size_t)(6 + 2 * Cp) * Pmax + (size_t)Lg * 12 + (size_t)Lg * Pmax); };
@@ -774,6 +774,7 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
     a.px = ctx->d_px.as<float>(); a.py = ctx->d_py.as<float>(); a.pz = ctx->d_pz.as<float>();
     a.pa = ctx->d_pa.as<float>(); a.pw = ctx->d_pw.as<float>();
     a.total = (int)ctx->total;
+    a.cq_rt = cq_actual;
     a.hint = hint_dev(ctx);
     a.absw = ctx->d_absw.as<float>();
     a.face_feat = ctx->d_face_feat.as<float>();
@@ -818,6 +819,7 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
             case 2: LAUNCH_UNARY(2); break;
             case 3: LAUNCH_UNARY(3); break;
             case 4: LAUNCH_UNARY(4); break;
+            case 5: LAUNCH_UNARY(5); break;
             default: FAIL("unsupported channel count");
         }
     }

@@ -127,6 +127,7 @@ struct UnaryArgs {
     const float* pcx; const float* pcy; const float* pcz;  // corner coordinates c
     const float* pa; const float* pw;   // packed source features / weights [Cp][total]
     int total;                          // stride of pa/pw channels
+    int cq_rt;                          // channel quads of the generic (CQ == 5) variant
     const int* hint_face;               // [Ns]
     const float* tref;                  // [Ns]
     const float* lab12;                 // [Ns][L][12]
@@ -147,7 +148,9 @@ __device__ __forceinline__ double group8_sum(double v) {
 
 template <int CQ>
 __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
-    constexpr int CP_ = CQ == 0 ? 1 : 4 * CQ;  // padded channel count
+    // padded channel count staged in shared memory; CQ == 5 is the generic variant (any channel count, a.cq_rt quads):
+    // source features / weights are then read straight from the packed global streams (coalesced, L1 resident)
+    constexpr int CP_ = CQ == 0 ? 1 : (CQ <= 4 ? 4 * CQ : 0);
     extern __shared__ float smem[];
     const int row = blockIdx.x / a.G, g = blockIdx.x - row * a.G;
     const int k = a.k_begin + row;
@@ -199,14 +202,48 @@ __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
         const int n = ico_descend_from(mtab, nlev, node_off + (face - (base << hshift)), al, be, ga);
         const int leaf = base * nleaf + (n - leaf_off);
         const float inv = __fdividef(1.0f, al + be + ga);
-        if (CQ == 0) {
+        if constexpr (CQ == 0) {
             // face-packed (f0_hi, f0_lo, f1-f0, f2-f0): t - tref = (f0_hi - tref) + f0_lo + wb (f1-f0) + wc (f2-f0)
             const float4 f = __ldg(reinterpret_cast<const float4*>(a.face_feat) + leaf);
             tb[j] = ((f.x - tref) + f.y) + ((be * inv) * f.z + (ga * inv) * f.w);
+        } else if constexpr (CQ > 4) {
+            // generic multivariate (more than 16 channels): two passes over the channels, re-gathering the target
+            const int cq = a.cq_rt;
+            const float4* ff = reinterpret_cast<const float4*>(a.face_feat) + (size_t)leaf * 3 * cq;
+            const float wa = al * inv, wb = be * inv, wc = ga * inv;
+            const float* paj = a.pa + s0 + i;
+            const float* pwj = a.pw + s0 + i;
+            float W = 0.f, Sa = 0.f, St = 0.f;
+            for (int q = 0; q < cq; q++) {
+                const float4 f0 = __ldg(ff + q), f1 = __ldg(ff + cq + q), f2 = __ldg(ff + 2 * cq + q);
+                const float t4[4] = {wa * f0.x + wb * f1.x + wc * f2.x, wa * f0.y + wb * f1.y + wc * f2.y,
+                                     wa * f0.z + wb * f1.z + wc * f2.z, wa * f0.w + wb * f1.w + wc * f2.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float w = pwj[(size_t)(4 * q + e) * a.total];
+                    W += w; Sa += w * paj[(size_t)(4 * q + e) * a.total]; St += w * t4[e];
+                }
+            }
+            if (W > 0.f) { Sa /= W; St /= W; }
+            float pr = 0.f, va = 0.f, vt = 0.f;
+            for (int q = 0; q < cq; q++) {
+                const float4 f0 = __ldg(ff + q), f1 = __ldg(ff + cq + q), f2 = __ldg(ff + 2 * cq + q);
+                const float t4[4] = {wa * f0.x + wb * f1.x + wc * f2.x, wa * f0.y + wb * f1.y + wc * f2.y,
+                                     wa * f0.z + wb * f1.z + wc * f2.z, wa * f0.w + wb * f1.w + wc * f2.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float w = pwj[(size_t)(4 * q + e) * a.total];
+                    const float da = paj[(size_t)(4 * q + e) * a.total] - Sa, dt = t4[e] - St;
+                    pr += w * da * dt; va += w * da * da; vt += w * dt * dt;
+                }
+            }
+            if (W > 0.f) { pr /= W; va /= W; vt /= W; }
+            const float rho = (va == 0.f || vt == 0.f) ? 0.f : pr / (sqrtf(va) * sqrtf(vt));
+            tb[j] = 1.0f - (1.0f + rho) * 0.5f;
         } else {
             // multivariate: Pearson across the channels of this one sample (src/DiscreteCostFunction.cpp:515-518)
             const float4* ff = reinterpret_cast<const float4*>(a.face_feat) + (size_t)leaf * 3 * CQ;
-            float t[CP_];
+            float t[CP_ > 0 ? CP_ : 1];
             const float wa = al * inv, wb = be * inv, wc = ga * inv;
 #pragma unroll
             for (int q = 0; q < CQ; q++) {

@@ -70,6 +70,8 @@ def test_patch_range_parameter_and_empty_patches(built):
     dict(data_level=5, cp_level=3, C=4, warp=0.3, deform_cp=0.2),
     dict(data_level=5, cp_level=2, C=3, warp=0.2),                      # C not a multiple of 4: padded channels
     dict(data_level=5, cp_level=2, C=7, warp=0.2),
+    dict(data_level=4, cp_level=2, C=16, warp=0.2),                     # largest register-resident variant
+    dict(data_level=4, cp_level=2, C=21, warp=0.2),                     # generic variant (> 16 channels)
     dict(data_level=6, cp_level=2, C=1, warp=0.3),                      # C1 of BASELINE.json (P ~ 1036: label groups)
     dict(data_level=6, cp_level=4, C=4, warp=0.3, deform_cp=0.2),       # C2 level 3
 ])
