@@ -146,6 +146,80 @@ __device__ __forceinline__ double group8_sum(double v) {
     return v;
 }
 
+// Univariate phase 2 with the number of remaining levels known at compile time and TWO items per thread in flight:
+// the two descents are independent dependency chains (each level waits on a 16-byte table read), so interleaving them
+// hides that latency without needing more resident warps.
+template <int NLEV>
+__device__ __forceinline__ void unary_items_uni(const UnaryArgs& a, const float* __restrict__ sK, const float4* __restrict__ rc4,
+                                                const float2* __restrict__ c2, float* __restrict__ tb, int items, int P, int face0,
+                                                float tref, int tid) {
+    const float invP = 1.0f / (float)max(P, 1);
+    const int hshift = 2 * a.hint.h;
+    const float4* __restrict__ mtab = a.ico.mtab;
+    const int leaf_off = a.ico.leaf_off, nleaf = a.ico.nleaf_per_base, node_off = a.hint.node_off;
+    const float4* __restrict__ ff = reinterpret_cast<const float4*>(a.face_feat);
+    for (int jb = 0; jb < items; jb += 512) {   // block-uniform trip count: the warp votes below see every lane
+        const int j0 = jb + tid, j1 = j0 + 256;
+        const bool has0 = j0 < items, has1 = j1 < items;
+        if (!__any_sync(0xffffffffu, has1)) {
+            // tail: nobody in this warp has a second item — plain single-item path
+            if (!has0) continue;
+            const int l = (int)(((float)j0 + 0.5f) * invP);
+            const int i = j0 - l * P;
+            const float4 rc = rc4[i];
+            const float2 cc = c2[i];
+            const float4* M = reinterpret_cast<const float4*>(sK + l * 12);
+            const float4 m0 = M[0], m1 = M[1], m2 = M[2];
+            float x = rc.w + (m2.y + (m0.x * rc.x + m0.y * rc.y + m0.z * rc.z));
+            float y = cc.x + (m2.z + (m0.w * rc.x + m1.x * rc.y + m1.y * rc.z));
+            float z = cc.y + (m2.w + (m1.z * rc.x + m1.w * rc.y + m2.x * rc.z));
+            int face = face0;
+            if (fminf(x, fminf(y, z)) < 0.f) face = ico_walk(a.hint, face0, x, y, z);
+            const int b = face >> hshift;
+            unsigned nn = (unsigned)(node_off + (face - (b << hshift)));
+#pragma unroll
+            for (int lv = 0; lv < NLEV; lv++) ico_descend_level(mtab, nn, x, y, z);
+            const float inv = __fdividef(1.0f, x + y + z);
+            const float4 f = __ldg(ff + (b * nleaf + ((int)nn - leaf_off)));
+            tb[j0] = ((f.x - tref) + f.y) + ((y * inv) * f.z + (z * inv) * f.w);
+            continue;
+        }
+        const int jj[2] = {has0 ? j0 : 0, has1 ? j1 : 0};   // inactive lanes recompute item 0 and do not store
+        float al[2], be[2], ga[2];
+        unsigned n[2];
+        int base[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int l = (int)(((float)jj[u] + 0.5f) * invP);
+            const int i = jj[u] - l * P;
+            const float4 rc = rc4[i];
+            const float2 cc = c2[i];
+            const float4* M = reinterpret_cast<const float4*>(sK + l * 12);
+            const float4 m0 = M[0], m1 = M[1], m2 = M[2];
+            al[u] = rc.w + (m2.y + (m0.x * rc.x + m0.y * rc.y + m0.z * rc.z));
+            be[u] = cc.x + (m2.z + (m0.w * rc.x + m1.x * rc.y + m1.y * rc.z));
+            ga[u] = cc.y + (m2.w + (m1.z * rc.x + m1.w * rc.y + m2.x * rc.z));
+            int face = face0;
+            if (fminf(al[u], fminf(be[u], ga[u])) < 0.f) face = ico_walk(a.hint, face0, al[u], be[u], ga[u]);
+            base[u] = face >> hshift;
+            n[u] = (unsigned)(node_off + (face - (base[u] << hshift)));
+        }
+#pragma unroll
+        for (int lv = 0; lv < NLEV; lv++) {
+            ico_descend_level(mtab, n[0], al[0], be[0], ga[0]);
+            ico_descend_level(mtab, n[1], al[1], be[1], ga[1]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int leaf = base[u] * nleaf + ((int)n[u] - leaf_off);
+            const float inv = __fdividef(1.0f, al[u] + be[u] + ga[u]);
+            const float4 f = __ldg(ff + leaf);
+            const float t = ((f.x - tref) + f.y) + ((be[u] * inv) * f.z + (ga[u] * inv) * f.w);
+            if (u == 0 ? has0 : has1) tb[jj[u]] = t;
+        }
+    }
+}
+
 template <int CQ>
 __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
     // padded channel count staged in shared memory; CQ == 5 is the generic variant (any channel count, a.cq_rt quads):
@@ -185,7 +259,21 @@ __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
     const float4* __restrict__ mtab = a.ico.mtab;
     const int leaf_off = a.ico.leaf_off, nleaf = a.ico.nleaf_per_base, node_off = a.hint.node_off;
 
-    for (int j = tid; j < items; j += 256) {
+    bool done = false;
+    if constexpr (CQ == 0) {
+        done = true;
+        switch (nlev) {  // uniform across the launch
+            case 1: unary_items_uni<1>(a, sK, rc4, c2, tb, items, P, face0, tref, tid); break;
+            case 2: unary_items_uni<2>(a, sK, rc4, c2, tb, items, P, face0, tref, tid); break;
+            case 3: unary_items_uni<3>(a, sK, rc4, c2, tb, items, P, face0, tref, tid); break;
+            case 4: unary_items_uni<4>(a, sK, rc4, c2, tb, items, P, face0, tref, tid); break;
+            case 5: unary_items_uni<5>(a, sK, rc4, c2, tb, items, P, face0, tref, tid); break;
+            case 6: unary_items_uni<6>(a, sK, rc4, c2, tb, items, P, face0, tref, tid); break;
+            case 7: unary_items_uni<7>(a, sK, rc4, c2, tb, items, P, face0, tref, tid); break;
+            default: done = false;
+        }
+    }
+    for (int j = done ? items : tid; j < items; j += 256) {
         const int l = (int)(((float)j + 0.5f) * invP);
         const int i = j - l * P;
         const float4 rc = rc4[i];
