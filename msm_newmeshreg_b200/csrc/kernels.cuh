@@ -172,6 +172,13 @@ __device__ __forceinline__ int bin_coord(const BinGrid& g, double x) {
     int c = (int)floor((x - g.lo) * g.inv_h);
     return min(g.G - 1, max(0, c));
 }
+// fp64 [V][3] vertices -> fp32 SoA (the patch pre-filter's copy)
+__global__ void __launch_bounds__(256) k_split_xyz(int V, const double* __restrict__ src, float* __restrict__ x, float* __restrict__ y,
+                                                   float* __restrict__ z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= V) return;
+    x[i] = (float)src[3 * i]; y[i] = (float)src[3 * i + 1]; z[i] = (float)src[3 * i + 2];
+}
 __global__ void __launch_bounds__(256) k_bin_count(BinGrid g, int V, const double* __restrict__ src, int* __restrict__ cell_of, int* __restrict__ counts) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= V) return;

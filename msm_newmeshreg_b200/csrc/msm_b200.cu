@@ -85,6 +85,7 @@ struct msm_ctx {
     int Vs = 0, Cs = 0, wrows = 0;
     bool multivariate = false;
     std::vector<double> h_src;
+    double src_bound = 0.0;  // max |coordinate| of the source mesh (sizes the patch voxel grid)
     DevBuf d_src, d_sxf, d_syf, d_szf, d_sfeat, d_swgt;
 
     // control-point grid
@@ -189,18 +190,6 @@ template <typename T>
 int upload(msm_ctx* ctx, DevBuf& b, const T* h, size_t n) {
     CK(b.ensure(std::max<size_t>(n, 1) * sizeof(T)));
     if (n) CK(cudaMemcpyAsync(b.p, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-    return 0;
-}
-
-int upload_xyz_soa_f(msm_ctx* ctx, const double* xyz, int n, DevBuf& bx, DevBuf& by, DevBuf& bz) {
-    CK(ctx->h_pin.ensure((size_t)n * 3 * sizeof(float)));
-    float* f = ctx->h_pin.as<float>();
-    for (int i = 0; i < n; i++) { f[i] = (float)xyz[3 * i]; f[n + i] = (float)xyz[3 * i + 1]; f[2 * n + i] = (float)xyz[3 * i + 2]; }
-    CK(bx.ensure((size_t)n * 4)); CK(by.ensure((size_t)n * 4)); CK(bz.ensure((size_t)n * 4));
-    CK(cudaMemcpyAsync(bx.p, f, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(by.p, f + n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(bz.p, f + 2 * n, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // pinned staging buffer is reused
     return 0;
 }
 
@@ -482,9 +471,18 @@ int msm_set_source(msm_ctx* ctx, const double* xyz, int V, const double* feat, i
 int msm_reset_source(msm_ctx* ctx, const double* xyz) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->Vs <= 0) FAIL("msm_set_source must be called first");
-    ctx->h_src.assign(xyz, xyz + (size_t)ctx->Vs * 3);
-    if (upload(ctx, ctx->d_src, xyz, (size_t)ctx->Vs * 3)) return 1;
-    if (upload_xyz_soa_f(ctx, xyz, ctx->Vs, ctx->d_sxf, ctx->d_syf, ctx->d_szf)) return 1;
+    // one host pass: keep a copy (exact-tie resolution in msm_build_patches needs the fp64 coordinates) and the
+    // bounding radius; the fp32 SoA copy used by the patch pre-filter is derived on the device
+    const size_t n3 = (size_t)ctx->Vs * 3;
+    ctx->h_src.resize(n3);
+    double rb = 0.0;
+    for (size_t i = 0; i < n3; i++) { const double v = xyz[i]; ctx->h_src[i] = v; rb = std::max(rb, std::fabs(v)); }
+    ctx->src_bound = rb;
+    if (upload(ctx, ctx->d_src, ctx->h_src.data(), n3)) return 1;
+    CK(ctx->d_sxf.ensure((size_t)ctx->Vs * 4)); CK(ctx->d_syf.ensure((size_t)ctx->Vs * 4)); CK(ctx->d_szf.ensure((size_t)ctx->Vs * 4));
+    k_split_xyz<<<(ctx->Vs + 255) / 256, 256, 0, ctx->stream>>>(ctx->Vs, ctx->d_src.as<double>(), ctx->d_sxf.as<float>(), ctx->d_syf.as<float>(),
+                                                               ctx->d_szf.as<float>());
+    KLAUNCH_CHECK();
     ctx->have_patches = false;
     return 0;
 }
@@ -620,10 +618,9 @@ int msm_build_patches(msm_ctx* ctx) {
     BinGrid bg{};
     bool binned = false;
     {
-        double maxsep = 0.0, Rb = 0.0;
+        double maxsep = 0.0;
         for (int k = ctx->k_begin; k < ctx->k_end; k++) maxsep = std::max(maxsep, ctx->h_maxsep[k]);
-        for (double v : ctx->h_src) Rb = std::max(Rb, std::fabs(v));
-        Rb = Rb * (1.0 + 1e-9) + 1e-6;
+        const double Rb = ctx->src_bound * (1.0 + 1e-9) + 1e-6;
         const double half = ctx->par.range * maxsep / 200.0;
         const char* brute = getenv("MSM_PATCH_BRUTE");
         if (half < 1.5 && !(brute && atoi(brute))) {
@@ -652,9 +649,17 @@ int msm_build_patches(msm_ctx* ctx) {
     if (binned) k_patch_binned<false><<<Ns, 128, 0, ctx->stream>>>(a, bg, 0);
     else k_patch<false><<<Ns, 256, 0, ctx->stream>>>(a);
     KLAUNCH_CHECK();
-    int n_unc = 0;
-    CK(cudaMemcpyAsync(&n_unc, ctx->d_unc_count.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // common case (no boundary ties): the offsets scan runs speculatively so that one host sync returns both the tie
+    // count and the totals
+    k_patch_scan<<<1, 1024, 0, ctx->stream>>>(Ns, ctx->d_counts.as<int>(), nullptr, ctx->d_off.as<int>(), ctx->d_totmax.as<int>());
+    KLAUNCH_CHECK();
+    CK(ctx->h_pin.ensure(16));
+    int* hp = ctx->h_pin.as<int>();
+    CK(cudaMemcpyAsync(hp, ctx->d_unc_count.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hp + 1, ctx->d_totmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    const int n_unc = hp[0];
+    int totmax[2] = {hp[1], hp[2]};
     if (n_unc > unc_cap) FAIL("msm_build_patches: too many boundary ties");
     bool have_acc = false;
     if (n_unc > 0) {
@@ -680,13 +685,12 @@ int msm_build_patches(msm_ctx* ctx) {
         if (upload(ctx, ctx->d_acc_idx, aidx.data(), aidx.size())) return 1;
         CK(cudaStreamSynchronize(ctx->stream));
         have_acc = true;
+        k_patch_scan<<<1, 1024, 0, ctx->stream>>>(Ns, ctx->d_counts.as<int>(), ctx->d_acc_off.as<int>(), ctx->d_off.as<int>(), ctx->d_totmax.as<int>());
+        KLAUNCH_CHECK();
+        CK(cudaMemcpyAsync(hp + 1, ctx->d_totmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        totmax[0] = hp[1]; totmax[1] = hp[2];
     }
-    k_patch_scan<<<1, 1024, 0, ctx->stream>>>(Ns, ctx->d_counts.as<int>(), have_acc ? ctx->d_acc_off.as<int>() : nullptr, ctx->d_off.as<int>(),
-                                              ctx->d_totmax.as<int>());
-    KLAUNCH_CHECK();
-    int totmax[2];
-    CK(cudaMemcpyAsync(totmax, ctx->d_totmax.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->total = totmax[0]; ctx->maxP = totmax[1];
     const size_t tot = std::max<long long>(ctx->total, 1);
     CK(ctx->d_idx.ensure(tot * 4));

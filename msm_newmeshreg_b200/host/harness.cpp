@@ -4,12 +4,20 @@
 // applyLabeling).  Compiled twice:
 //   * libmsm_host.so  (product): model + GPU-backed cost functions only;
 //   * oracle/_ref/libref_optim.so (test infrastructure, -DWITH_REF_OPTIM): additionally the UNMODIFIED vendored optimisers
-//     from /root/reference/include (FastPD, ELC/HOCR, Fusion), compiled where they lie against these FSL-free headers.
+//     from /root/reference/include (FastPD, ELC/HOCR, Fusion), compiled where they lie against these FSL-free headers;
+//   * oracle/_ref/libref_cost.so (test infrastructure, -DWITH_REF_COST -DWITH_REF_OPTIM): the SAME entry points over the
+//     REFERENCE'S OWN DiscreteModel / DiscreteCostFunction classes (src/*.cpp compiled where they lie, oracle/Makefile
+//     `refcost`) — the CPU reference the GPU path and the oracle port are pinned against.
 #include <cstring>
 #include <memory>
 
+#ifdef WITH_REF_COST
+#include "DiscreteGroupModel.h"  // /root/reference/src (the product mirror is NOT on the include path of this build)
+#include "DiscreteModel.h"
+#else
 #include "src/DiscreteGroupModel.h"
 #include "src/DiscreteModel.h"
+#endif
 
 #ifdef WITH_REF_OPTIM
 #define HAS_FPD
@@ -22,17 +30,79 @@ using namespace newmeshreg;
 
 namespace {
 thread_local std::string g_err;
-struct ModelBox {
-    std::shared_ptr<NonLinearSRegDiscreteModel> model;
-    std::shared_ptr<DiscreteGroupModel> group;
-    myparam params;
-    newresampler::Mesh target, source;
+
+// The few places where this file needs more than the reference's class surface offers (raw-array meshes, in-memory
+// features, reading the label set back) go through the adapters below, one set per build.
+#ifdef WITH_REF_COST
+newresampler::Mesh mesh_from(const double* xyz, int nv, const int* tris, int nf) {
+    orc::Mesh m;
+    m.V.resize(nv); m.F.resize(nf);
+    for (int i = 0; i < nv; i++) m.V[i] = orc::Pt(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    for (int t = 0; t < nf; t++) m.F[t] = {tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]};
+    m.build_adjacency();
+    return newresampler::Mesh(m);
+}
+std::vector<double> coords_of(const newresampler::Mesh& m) {
+    std::vector<double> o((size_t)m.nvertices() * 3);
+    for (int i = 0; i < m.nvertices(); i++) { const newresampler::Point& p = m.get_coord(i); o[3 * i] = p.X; o[3 * i + 1] = p.Y; o[3 * i + 2] = p.Z; }
+    return o;
+}
+std::vector<int> faces_of(const newresampler::Mesh& m) {
+    std::vector<int> o((size_t)m.ntriangles() * 3);
+    for (int t = 0; t < m.ntriangles(); t++) for (int j = 0; j < 3; j++) o[3 * t + j] = m.get_triangle_vertexID(t, j);
+    return o;
+}
+// The reference's featurespace only has file-name constructors (src/featurespace.h:14-15; featurespace.cc needs FSL
+// I/O and is not compiled): oracle/ref_cost_ext.cpp defines them to take their matrices from this registry instead.
+}  // namespace
+namespace refcost { std::map<std::string, std::shared_ptr<MISCMATHS::BFMatrix>>& feature_registry(); }
+namespace {
+std::shared_ptr<featurespace> make_features(const double* input, int Vin, const double* ref, int Vref, int dim) {
+    auto put = [&](const char* key, const double* d, int V) {
+        auto M = std::make_shared<MISCMATHS::FullBFMatrix>(dim, V);
+        for (int c = 0; c < dim; c++) for (int v = 0; v < V; v++) M->Set(c + 1, v + 1, d[(size_t)c * V + v]);
+        refcost::feature_registry()[key] = M;
+    };
+    put("harness:input", input, Vin);
+    put("harness:reference", ref, Vref);
+    return std::make_shared<featurespace>(std::string("harness:input"), std::string("harness:reference"));
+}
+struct CostFunctionPeek : NonLinearSRegDiscreteCostFunction { using NonLinearSRegDiscreteCostFunction::_sourceinrange; };
+struct ModelT : NonLinearSRegDiscreteModel {
+    using NonLinearSRegDiscreteModel::NonLinearSRegDiscreteModel;
+    const std::vector<newresampler::Point>& get_labels() const { return m_labels; }
+    // the per-control-point source patches built by get_source_data (src/DiscreteCostFunction.cpp:394-410,458-481)
+    const std::vector<std::vector<int>>& patches() const { return static_cast<const CostFunctionPeek*>(costfct.get())->_sourceinrange; }
 };
+myparam default_parameters() {  // one resolution level (src/mesh_registration.cpp:491-556,689-715,815-847)
+    myparam P;
+    P["lambda"] = 0.1f;  P["exponent"] = 2.0f;  P["weight"] = false;  P["anorm"] = false;
+    P["shearmodulus"] = 0.4f;  P["bulkmodulus"] = 1.6f;  P["kexponent"] = 2.0f;  P["range"] = 1.0f;
+    P["simmeasure"] = 2;  P["verbosity"] = false;  P["regularisermode"] = 1;  P["numthreads"] = 1;
+    P["dOPT"] = std::string("FastPD");  P["SGres"] = 4;  P["CPres"] = 2;  P["multivariate"] = false;
+    P["outdir"] = std::string("");  P["TriLikelihood"] = false;  P["rescalelabels"] = false;  P["labeldist"] = 0.5f;
+    P["iters"] = 3;
+    return P;
+}
+#else
+using ModelT = NonLinearSRegDiscreteModel;
 newresampler::Mesh mesh_from(const double* xyz, int nv, const int* tris, int nf) {
     newresampler::Mesh m;
     m.set(xyz, nv, tris, nf);
     return m;
 }
+std::vector<double> coords_of(const newresampler::Mesh& m) { return m.coords(); }
+std::vector<int> faces_of(const newresampler::Mesh& m) { return m.faces(); }
+std::shared_ptr<featurespace> make_features(const double* input, int Vin, const double* ref, int Vref, int dim) {
+    return std::make_shared<featurespace>(input, Vin, ref, Vref, dim);
+}
+#endif
+
+struct ModelBox {
+    std::shared_ptr<ModelT> model;
+    myparam params;
+    newresampler::Mesh target, source;
+};
 template <typename F>
 int guard(F&& f) {
     try { f(); return 0; }
@@ -92,7 +162,7 @@ void msmhost_icosphere_counts(int level, int* nv, int* nf) {
 void msmhost_icosphere(int level, double radius, double* xyz, int* tris) {
     newresampler::Mesh m = newresampler::make_mesh_from_icosa(level);
     newresampler::true_rescale(m, radius);
-    auto c = m.coords(); auto f = m.faces();
+    auto c = coords_of(m); auto f = faces_of(m);
     std::memcpy(xyz, c.data(), c.size() * sizeof(double));
     std::memcpy(tris, f.data(), f.size() * sizeof(int));
 }
@@ -107,7 +177,7 @@ void* msmhost_model_create(double lambda, double rexp, double mu, double kappa, 
     P["kexponent"] = (float)kexp; P["range"] = (float)range; P["simmeasure"] = simmeasure; P["regularisermode"] = rmode;
     P["weight"] = dweight != 0; P["anorm"] = anorm != 0; P["SGres"] = sgres; P["CPres"] = cpres; P["labeldist"] = (float)labeldist;
     P["multivariate"] = multivariate != 0; P["dOPT"] = std::string(dopt); P["numthreads"] = threads;
-    if (guard([&] { b->model = std::make_shared<NonLinearSRegDiscreteModel>(P); })) { delete b; return nullptr; }
+    if (guard([&] { b->model = std::make_shared<ModelT>(P); })) { delete b; return nullptr; }
     return b;
 }
 void msmhost_model_destroy(void* h) { delete (ModelBox*)h; }
@@ -118,7 +188,7 @@ int msmhost_model_set_data(void* h, const double* txyz, int Vt, const int* ttris
     return guard([&] {
         b->target = mesh_from(txyz, Vt, ttris, Ft);
         b->source = mesh_from(sxyz, Vs, stris, Fs);
-        b->model->set_featurespace(std::make_shared<featurespace>(input, Vs, ref, Vt, C));
+        b->model->set_featurespace(make_features(input, Vs, ref, Vt, C));
         b->model->set_meshspace(b->target, b->source);
     });
 }
@@ -152,7 +222,21 @@ int msmhost_model_reset_cpgrid(void* h, const double* cxyz) {  // :393
         b->model->reset_CPgrid(g);
     });
 }
-int msmhost_model_setup(void* h) { auto* b = (ModelBox*)h; return guard([&] { b->model->setupCostFunction(); }); }  // :337
+int msmhost_model_setup(void* h) {  // :330-337
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+#ifdef WITH_REF_COST
+        // the driver hands the cost function unit weights when no weighting is supplied (:330-334); the reference's
+        // own initialize() would otherwise ReSize them to zeros (src/DiscreteCostFunction.cpp:115-116).  The product
+        // mirror defaults to unit weights by itself (host/src/DiscreteCostFunction.h initialize()).
+        NEWMAT::Matrix CombinedWeight;
+        CombinedWeight.resize(1, b->source.nvertices());
+        CombinedWeight = 1;
+        b->model->setupCostFunctionWeighting(CombinedWeight);
+#endif
+        b->model->setupCostFunction();
+    });
+}
 int msmhost_model_unary(void* h, double* out) {  // :347 computeUnaryCosts + the table
     auto* b = (ModelBox*)h;
     return guard([&] {
@@ -164,7 +248,7 @@ int msmhost_model_unary(void* h, double* out) {  // :347 computeUnaryCosts + the
 int msmhost_model_get(void* h, double* cpgrid, double* labels, int* pairs, int* triplets) {
     auto* b = (ModelBox*)h;
     return guard([&] {
-        if (cpgrid) { auto c = b->model->get_CPgrid().coords(); std::memcpy(cpgrid, c.data(), c.size() * sizeof(double)); }
+        if (cpgrid) { auto c = coords_of(b->model->get_CPgrid()); std::memcpy(cpgrid, c.data(), c.size() * sizeof(double)); }
         if (labels) {
             const auto& l = b->model->get_labels();
             for (size_t i = 0; i < l.size(); i++) { labels[3 * i] = l[i].X; labels[3 * i + 1] = l[i].Y; labels[3 * i + 2] = l[i].Z; }
@@ -177,7 +261,14 @@ int msmhost_model_get(void* h, double* cpgrid, double* labels, int* pairs, int* 
 int msmhost_model_costs(void* h, int kind, int n, const int* q, double* out) {
     auto* b = (ModelBox*)h;
     return guard([&] {
-#pragma omp parallel for
+#ifdef WITH_REF_COST
+        // only the reference's triplet virtual is re-entrant: computeUnaryCost keeps patch means in the shared `sim`
+        // member (src/similarities.h:38) and computePairwiseCost moves _CPgrid vertices and puts them back (:269-292)
+        const bool parallel = kind == 2;
+#else
+        const bool parallel = true;
+#endif
+#pragma omp parallel for if (parallel)
         for (int i = 0; i < n; i++) {
             if (kind == 0) out[i] = b->model->computeUnaryCost(q[2 * i], q[2 * i + 1]);
             else if (kind == 1) out[i] = b->model->computePairwiseCost(q[3 * i], q[3 * i + 1], q[3 * i + 2]);
@@ -200,28 +291,47 @@ int msmhost_model_apply_labeling(void* h, double* new_cpgrid) {  // :386
     auto* b = (ModelBox*)h;
     return guard([&] {
         b->model->applyLabeling();
-        auto c = b->model->get_CPgrid().coords();
+        auto c = coords_of(b->model->get_CPgrid());
         std::memcpy(new_cpgrid, c.data(), c.size() * sizeof(double));
     });
 }
+#ifndef WITH_REF_COST
 // borrowed handle of the cost function's device context (device-resident table variants of the C ABI)
 void* msmhost_model_context(void* h) { return ((ModelBox*)h)->model->getNonLinearCostFunction()->context(); }
 int msmhost_model_triplet_moves(void* h, const int* labeling, int alpha, double* out) {
     auto* b = (ModelBox*)h;
     return guard([&] { b->model->getNonLinearCostFunction()->computeTripletMoves(labeling, alpha, out); });
 }
+#else
+// the reference has no batched move evaluation: the same [L][T][8] / [T][8] layout from its per-element virtual
+// (include/Fusion/Fusion.h:187-194 bit order: bit2 -> A, bit1 -> B, bit0 -> C take the proposal label)
+int msmhost_model_triplet_moves(void* h, const int* labeling, int alpha, double* out) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        const int T = b->model->getNumTriplets(), L = b->model->getNumLabels();
+        const int* tr = b->model->getTriplets();
+        const int a0 = alpha < 0 ? 0 : alpha, a1 = alpha < 0 ? L : alpha + 1;
+#pragma omp parallel for collapse(2)
+        for (int a = a0; a < a1; a++)
+            for (int t = 0; t < T; t++) {
+                const int cur[3] = {labeling[tr[3 * t]], labeling[tr[3 * t + 1]], labeling[tr[3 * t + 2]]};
+                double* o = out + ((size_t)(a - a0) * T + t) * 8;
+                for (int m = 0; m < 8; m++)
+                    o[m] = b->model->computeTripletCost(t, (m & 4) ? a : cur[0], (m & 2) ? a : cur[1], (m & 1) ? a : cur[2]);
+            }
+    });
+}
+#endif
 
 // ---- mesh warp -----------------------------------------------------------------------------------
 // barycentric_mesh_interpolation(SPH_up, SPH_low_init, SPH_low_final) on raw arrays; `up` is updated in place
 int msmhost_mesh_interpolate(double* up, int m, const double* init_xyz, int nv, const int* tris, int nf, const double* final_xyz) {
     return guard([&] {
-        newresampler::Mesh U, A, B;
-        std::vector<int> none;
-        U.set(up, m, none.data(), 0);
-        A = mesh_from(init_xyz, nv, tris, nf);
-        B = mesh_from(final_xyz, nv, tris, nf);
+        newresampler::Mesh U = mesh_from(up, m, nullptr, 0);
+        newresampler::Mesh A = mesh_from(init_xyz, nv, tris, nf);
+        newresampler::Mesh B = mesh_from(final_xyz, nv, tris, nf);
         newresampler::barycentric_mesh_interpolation(U, A, B);
-        auto c = U.coords();
+        auto c = coords_of(U);
         std::memcpy(up, c.data(), c.size() * sizeof(double));
     });
 }
@@ -229,10 +339,78 @@ int msmhost_unfold(double* xyz, int nv, const int* tris, int nf) {
     return guard([&] {
         newresampler::Mesh M = mesh_from(xyz, nv, tris, nf);
         unfold(M, false);
-        auto c = M.coords();
+        auto c = coords_of(M);
         std::memcpy(xyz, c.data(), c.size() * sizeof(double));
     });
 }
+
+#ifdef WITH_REF_COST
+// ---- the reference's DiscreteGroupCostFunction (src/DiscreteGroupCostFunction.{h,cpp}), same flat interface as the
+// oracle port's orc_gc_* (oracle/oracle_capi.cpp) so the two can be compared query by query -----------------------------
+namespace {
+struct GroupBox {
+    DiscreteGroupCostFunction cf;
+    std::vector<int> triplets, pairs;
+    int L = 0;
+};
+}  // namespace
+// patch lists of the last setupCostFunction: sizes[N]; idx (may be NULL) receives the concatenated source vertex ids
+int ref_model_patches(void* h, int* sizes, int* idx) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        size_t o = 0;
+        const auto& P = b->model->patches();
+        for (size_t k = 0; k < P.size(); k++) {
+            sizes[k] = (int)P[k].size();
+            if (idx) std::copy(P[k].begin(), P[k].end(), idx + o);
+            o += P[k].size();
+        }
+    });
+}
+void* ref_gc_create() { return new GroupBox(); }
+void ref_gc_destroy(void* h) { delete (GroupBox*)h; }
+int ref_gc_set(void* h, double lambda, double rexp, double mu, double kappa, int S, const double* cp_xyz /*S*N*3*/, int N, const int* cp_tris,
+               int T, const double* orig_xyz /*N*3*/, const double* labels, int L, const double* ROT /*S*N*9*/, const int* triplets /*S*T*3*/) {
+    auto* g = (GroupBox*)h;
+    return guard([&] {
+        myparam P = default_parameters();
+        P["lambda"] = (float)lambda; P["exponent"] = (float)rexp; P["shearmodulus"] = (float)mu; P["bulkmodulus"] = (float)kappa;
+        g->cf.set_parameters(P);
+        const newresampler::Mesh orig = mesh_from(orig_xyz, N, cp_tris, T);
+        g->cf.set_meshes(orig, orig, orig, S);                                     // src/DiscreteGroupModel.cpp:139
+        for (int s = 0; s < S; s++) g->cf.reset_CPgrid(mesh_from(cp_xyz + (size_t)s * N * 3, N, cp_tris, T), s);
+        std::vector<newresampler::Point> lab(L);
+        for (int i = 0; i < L; i++) lab[i] = newresampler::Point(labels[3 * i], labels[3 * i + 1], labels[3 * i + 2]);
+        std::vector<NEWMAT::Matrix> rot((size_t)S * N, NEWMAT::Matrix(3, 3));
+        for (size_t k = 0; k < rot.size(); k++)
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) rot[k](i + 1, j + 1) = ROT[9 * k + 3 * i + j];
+        g->cf.set_labels(lab, rot);
+        g->L = L;
+        g->triplets.assign(triplets, triplets + (size_t)S * T * 3);
+        g->cf.initialize(S * N, L, (int)g->pairs.size() / 2, S * T);
+        g->cf.setTriplets(g->triplets.data());
+    });
+}
+int ref_gc_triplet_costs(void* h, int n, const int* q, double* out) {
+    auto* g = (GroupBox*)h;
+    return guard([&] { for (int i = 0; i < n; i++) out[i] = g->cf.computeTripletCost(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]); });
+}
+int ref_gc_set_patches(void* h, int nmaps, const long long* off, const int* keys, const double* vals, const int* pairs, int np) {
+    auto* g = (GroupBox*)h;
+    return guard([&] {
+        std::vector<std::map<int, double>> pd(nmaps);
+        for (int m = 0; m < nmaps; m++)
+            for (long long e = off[m]; e < off[m + 1]; e++) pd[m][keys[e]] = vals[e];
+        g->cf.set_patch_data(pd);
+        g->pairs.assign(pairs, pairs + 2 * (size_t)np);
+        g->cf.setPairs(g->pairs.data());
+    });
+}
+int ref_gc_pair_costs(void* h, int n, const int* q, int /*L*/, double* out) {
+    auto* g = (GroupBox*)h;
+    return guard([&] { for (int i = 0; i < n; i++) out[i] = g->cf.computePairwiseCost(q[3 * i], q[3 * i + 1], q[3 * i + 2]); });
+}
+#endif
 
 #ifdef WITH_REF_OPTIM
 // ---- unmodified reference optimisers ------------------------------------------------------------------------------
@@ -285,7 +463,7 @@ int ref_run_discrete_opt(void* h, int iters, int threads, double* source_xyz, in
             energy = newenergy;
             seconds_warp[iter - 1] = omp_get_wtime() - t2;
         }
-        auto c = source.coords();
+        auto c = coords_of(source);
         std::memcpy(source_xyz, c.data(), c.size() * sizeof(double));
     });
     return st == 0 ? done : -1;

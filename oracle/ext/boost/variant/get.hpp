@@ -1,0 +1,3 @@
+// forwarding header: boost::variant / boost::get stand-in over std::variant; see ../../fsl_ext.h
+#pragma once
+#include "../../fsl_ext.h"

@@ -1,0 +1,3 @@
+// forwarding header: the reference includes "newresampler/octree.h" from FSL ([EXT], absent here); see ../fsl_ext.h
+#pragma once
+#include "../fsl_ext.h"

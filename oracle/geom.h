@@ -4,7 +4,9 @@
 // oracle/geom.h : FSL-free restatement of the external geometry semantics the reference hot path relies on
 // (SURVEY.md §0.3 assumptions A1-A7).  The reference links FSL `newresampler` (src/Makefile:5, no version pin),
 // which is NOT present under /root/reference, so these are restatements of its published behaviour anchored on
-// the reference's own call sites.  PARITY UNPINNED: the reference ships no tests/golden vectors at this boundary.
+// the reference's own call sites — the one part of the oracle that cannot be pinned against reference code (the
+// library is a dependency absent from the tree); the reference build of oracle/_ref/libref_cost.so uses the SAME
+// functions through oracle/ext/fsl_ext.h, so these semantics exist exactly once.
 //
 // Everything is double precision, single-thread semantics, no global state.
 #pragma once

@@ -1,4 +1,5 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/oracle.h).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/oracle.h).  Pinned against the reference's own sources compiled in place
+// (oracle/_ref/libref_cost.so, tests/test_reference_pin.py).
 #include "oracle.h"
 
 #include <omp.h>

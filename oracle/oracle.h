@@ -1,6 +1,10 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/geom.h header).  PARITY UNPINNED: the reference has no tests,
-// golden vectors or fixtures for this path and cannot be compiled here (FSL absent), so this
-// CPU restatement is pinned only by the self-made known-answer tests in tests/test_oracle_*.py.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle/geom.h header).  PARITY PINNED AGAINST THE REFERENCE ITSELF: the
+// reference has no tests or golden vectors for this path, but its own cost-evaluation sources
+// (src/DiscreteCostFunction.cpp, similarities.cc, reg_tools.cpp, DiscreteModel.cpp, DiscreteGroup*.cpp) compile
+// unmodified where they lie once the absent FSL libraries are stood in for (oracle/ext/fsl_ext.h ->
+// oracle/_ref/libref_cost.so, oracle/Makefile `refcost`).  tests/test_reference_pin.py holds this port to that build
+// (unary 1e-12 abs, strain / pairwise 1e-9 rel, patch lists / cliques / label sets bit exact) and
+// tests/golden/small_tables.npz is generated from it.  Not pinnable: the [EXT] geometry of oracle/geom.h.
 //
 // oracle/oracle.h : double-precision, single-thread-semantics restatement of the reference hot path:
 //   * model glue          src/DiscreteModel.cpp:38-162,188-294   (MAXSEP, label grid, rotations, pairs, triplets)

@@ -2,7 +2,7 @@
 
 ctypes binding of oracle/liborc.so (the CPU restatement of the reference hot path, oracle/oracle.h).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
-PARITY UNPINNED: the reference has no tests or golden vectors for this path.
+Pinned against the reference's own sources compiled in place (oracle/pyrefcost.py, tests/test_reference_pin.py).
 """
 import ctypes as C
 import os

@@ -1,8 +1,10 @@
-"""Generates tests/golden/small_tables.npz from the ORACLE (oracle/liborc.so).
+"""Generates tests/golden/small_tables.npz from THE REFERENCE ITSELF: oracle/_ref/libref_cost.so = the reference's own
+src/DiscreteCostFunction.cpp / similarities.cc / reg_tools.cpp / DiscreteModel.cpp compiled unmodified where they lie
+(oracle/Makefile `refcost`; the absent FSL libraries stood in for by oracle/ext/fsl_ext.h), run single-threaded (its
+multi-threaded unary loop is racy, see tests/test_reference_pin.py).
 
-The reference itself cannot run here (FSL is absent: SURVEY.md §0.2) and ships no golden vectors, so these fixtures
-pin the oracle against regressions and give the GPU tests a second, frozen comparison point; they do NOT pin the
-oracle to the real reference (PARITY UNPINNED).  Re-run:  python tests/golden/make_golden.py
+The committed fixture is what travels: the CPU test checks the oracle port against it, the GPU test the CUDA path.
+Re-run (dev container only, needs /root/reference at build time):  python tests/golden/make_golden.py
 """
 import os
 import sys
@@ -21,7 +23,13 @@ CASES = {
 }
 
 
+def queries(P):
+    rng = np.random.default_rng(99)
+    return np.stack([rng.integers(0, P.T, 400), rng.integers(0, P.L, 400), rng.integers(0, P.L, 400), rng.integers(0, P.L, 400)], 1).astype(np.int32)
+
+
 def tables(name):
+    """The ORACLE's version of one case (what test_host_cpu checks against the committed reference output)."""
     kw, params = CASES[name]
     P = pb.make_problem(**kw)
     cf = pb.oracle_costfunction(P, params=params)
@@ -31,19 +39,52 @@ def tables(name):
     out["patch_sizes"] = np.array([len(p) for p in patches], np.int32)
     out["patch_idx"] = np.concatenate(patches).astype(np.int32)
     out["unary"] = cf.unary_costs()
-    rng = np.random.default_rng(99)
-    q = np.stack([rng.integers(0, P.T, 400), rng.integers(0, P.L, 400), rng.integers(0, P.L, 400), rng.integers(0, P.L, 400)], 1).astype(np.int32)
-    out["triplet_q"] = q
-    out["triplet_costs"] = cf.triplet_costs(q)
+    out["triplet_q"] = queries(P)
+    out["triplet_costs"] = cf.triplet_costs(out["triplet_q"])
     cfp = pb.oracle_costfunction(P, params=dict(params, rmode=1), cliques="pairs")
     out["pair_table_first8"] = cfp.pair_table()[:8]
+    return P, out
+
+
+def reference_tables(name):
+    """The same case through the reference's own classes (src/mesh_registration.cpp:66,86,336-337,347 call order)."""
+    from oracle import pyrefcost
+    kw, params = CASES[name]
+    P = pb.make_problem(**kw)
+
+    def model(**over):
+        pr = dict(pb.DEFAULT_PARAMS); pr.update(params); pr.update(over)
+        m = pyrefcost.model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=P.C > 1, threads=1, **pr)
+        m.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref)
+        m.initialize()
+        m.reset_meshspace(P.sxyz)
+        m.reset_cpgrid(P.cxyz)
+        m.setup()
+        return m
+
+    m = model()
+    assert np.array_equal(m.labels(), P.labels) and np.array_equal(m.triplets(), P.triplets)
+    out = {}
+    patches = pyrefcost.patches(m)
+    out["patch_sizes"] = np.array([len(p) for p in patches], np.int32)
+    out["patch_idx"] = np.concatenate(patches).astype(np.int32)
+    out["unary"] = m.unary()
+    out["triplet_q"] = queries(P)
+    out["triplet_costs"] = m.costs("triplet", out["triplet_q"])
+    m.close()
+    mp = model(rmode=1, dopt="FastPD")
+    assert np.array_equal(mp.pairs(), P.pairs)
+    L = mp.L
+    q = np.array([[p, la, lb] for p in range(8) for lb in range(L) for la in range(L)], np.int32)   # [P][lb][la] (:303)
+    out["pair_table_first8"] = mp.costs("pair", q).reshape(8, L, L)
+    mp.close()
     return P, out
 
 
 if __name__ == "__main__":
     blob = {}
     for name in CASES:
-        _, out = tables(name)
+        _, out = reference_tables(name)
         for k, v in out.items():
             blob[f"{name}/{k}"] = v
     np.savez_compressed(os.path.join(HERE, "small_tables.npz"), **blob)

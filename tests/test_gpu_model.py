@@ -113,3 +113,88 @@ def test_outer_iterations_labellings_identical(built):
         cp[sing] = new_gpu[sing]
         m.reset_cpgrid(cp)
     m.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU path against THE REFERENCE ITSELF (oracle/_ref/libref_cost.so: the reference's own sources compiled in place)
+# ---------------------------------------------------------------------------------------------------------------------
+def _ref_model(P, **kw):
+    from oracle import pyrefcost
+    pr = dict(pb.DEFAULT_PARAMS); pr.update(kw)
+    m = pyrefcost.model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=P.C > 1, threads=1, **pr)
+    m.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref)
+    m.initialize()
+    m.reset_meshspace(P.sxyz)
+    return m
+
+
+def _have_refcost():
+    from oracle import pyrefcost
+    return pyrefcost.available()
+
+
+@pytest.mark.skipif(not _have_refcost(), reason="oracle/_ref/libref_cost.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("C", [1, 4])
+def test_gpu_model_equals_reference_model(built, C):
+    """Same driver call sequence (src/mesh_registration.cpp:66,86,336-337,347) on the GPU-backed mirror classes and on the
+    reference's own classes: unary table 1e-5 rel (fp32 path), strain / total 1e-9 rel (fp64 paths), move tables."""
+    P = pb.make_problem(4, 2, C, seed=61 + C, warp=0.3, deform_cp=0.12)
+    g, r = _model(P, rmode=3), _ref_model(P, rmode=3)
+    for m in (g, r):
+        m.reset_cpgrid(P.cxyz); m.setup()
+    assert (g.N, g.L, g.T) == (r.N, r.L, r.T)
+    assert np.array_equal(g.labels(), r.labels()) and np.array_equal(g.triplets(), r.triplets())
+    Ug, Ur = g.unary(), r.unary()
+    assert pb.rel_err(Ug, Ur, 1e-2).max() < 1e-5
+    rng = np.random.default_rng(C)
+    q = np.stack([rng.integers(0, P.T, 3000)] + [rng.integers(0, P.L, 3000) for _ in range(3)], 1).astype(np.int32)
+    assert pb.rel_err(g.costs("triplet", q), r.costs("triplet", q), 1e-9).max() < 1e-5   # look-up table is fp32
+    lab = rng.integers(0, P.L, P.N).astype(np.int32)
+    assert pb.rel_err(g.triplet_moves(lab, 5), r.triplet_moves(lab, 5), 1e-9).max() < 1e-9
+    for m in (g, r):
+        m.set_labeling(lab)
+    assert abs(g.total() - r.total()) <= 1e-5 * abs(r.total())
+    assert np.abs(g.apply_labeling() - r.apply_labeling()).max() < 1e-9
+    g.close(); r.close()
+
+
+@pytest.mark.skipif(not _have_refcost(), reason="oracle/_ref/libref_cost.so not built (needs /root/reference at build time)")
+def test_gpu_pairwise_model_equals_reference_model(built):
+    P = pb.make_problem(3, 2, 1, seed=66, warp=0.2, deform_cp=0.1)
+    g, r = _model(P, rmode=1, dopt="FastPD"), _ref_model(P, rmode=1, dopt="FastPD")
+    for m in (g, r):
+        m.reset_cpgrid(P.cxyz); m.setup()
+    assert np.array_equal(g.pairs(), r.pairs())
+    rng = np.random.default_rng(1)
+    q = np.stack([rng.integers(0, g.P, 3000), rng.integers(0, P.L, 3000), rng.integers(0, P.L, 3000)], 1).astype(np.int32)
+    a, b = g.costs("pair", q), r.costs("pair", q)
+    assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-3)       # identity-label acos noise, see test_gpu_parity
+    g.close(); r.close()
+
+
+@pytest.mark.skipif(not (_have_refcost() and pyref.available()), reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("dopt,rmode", [("HOCR", 3), ("FastPD", 1)])
+def test_run_discrete_opt_gpu_equals_reference_end_to_end(built, dopt, rmode):
+    """Mesh_registration::run_discrete_opt (src/mesh_registration.cpp:316-397), three outer iterations: the reference all on
+    the CPU (its cost functions, its optimisers, its unfold) against the same driver over the GPU-backed cost functions.
+    Labellings identical at every iteration; warped source vertices within 1e-4 (north_star)."""
+    from msm_newmeshreg_b200 import host
+    from oracle import pyrefcost
+    P = pb.make_problem(4, 2, 1, seed=71, warp=0.0)
+    pr = dict(pb.DEFAULT_PARAMS); pr.update(rmode=rmode, dopt=dopt)
+    g = host.Model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, _lib_override=pyref.lib(), **pr)
+    r = pyrefcost.model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, threads=1, **pr)
+    for m in (g, r):
+        m.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref); m.initialize()
+    start = pb.smooth_warp(P.txyz, 171, 0.2 * P.mvd)
+    sg, lg, eg, _ = pyref.run_discrete_opt(g, start, 3, threads=4)
+    sr, lr, er, _ = pyrefcost.run_discrete_opt(r, start, 3, threads=1)
+    assert len(lg) == len(lr)
+    sing = pb.singular_nodes(P)
+    keep = np.ones(P.N, bool); keep[sing] = False
+    for it, (a, b) in enumerate(zip(lg, lr)):
+        assert np.array_equal(a[keep], b[keep]), f"iteration {it + 1}: {(a != b).sum()} labels differ"
+    assert np.allclose(eg, er, rtol=1e-5)
+    d_sing = np.linalg.norm(P.txyz - P.cxyz0[sing[0]], axis=1) if len(sing) else np.full(len(P.txyz), 1e9)
+    assert np.abs(sg - sr)[d_sing > 2.5 * P.mvdmax].max() < 1e-4
+    g.close(); r.close()
