@@ -114,7 +114,9 @@ __device__ __forceinline__ void ico_descend_level(const float4* __restrict__ mta
     const float va = (cb_ || cc_) ? al : fabsf(sa);
     const float vb = (ca || cc_) ? be : fabsf(sb);
     const float vc = (ca || cb_) ? ga : fabsf(sc);
-    al = va * m.x; be = vb * m.y; ga = vc * m.z;
+    // __fmul_rn: never contracted into the next level's additions — whether ptxas fuses depends on the surrounding code,
+    // and the same item must give the same bits at every call site (label-group size / shard independence)
+    al = __fmul_rn(va, m.x); be = __fmul_rn(vb, m.y); ga = __fmul_rn(vc, m.z);
 }
 
 template <int NLEV>
@@ -150,9 +152,9 @@ __device__ __forceinline__ int ico_walk(const HintDev& hd, int face, float& al, 
         // three 16-byte rows per (face, edge): the 3x3 change of corner coordinates; row 0 carries the neighbour id
         const float4* T = hd.hT + (unsigned)(face * 3 + e) * 3u;
         const float4 r0 = __ldg(T), r1 = __ldg(T + 1), r2 = __ldg(T + 2);
-        const float x = r0.x * al + r0.y * be + r0.z * ga;
-        const float y = r1.x * al + r1.y * be + r1.z * ga;
-        const float z = r2.x * al + r2.y * be + r2.z * ga;
+        const float x = fmaf(r0.z, ga, fmaf(r0.y, be, r0.x * al));   // contraction spelled out: same bits at every call site
+        const float y = fmaf(r1.z, ga, fmaf(r1.y, be, r1.x * al));
+        const float z = fmaf(r2.z, ga, fmaf(r2.y, be, r2.x * al));
         face = __float_as_int(r0.w);
         al = x; be = y; ga = z;
     }

@@ -770,6 +770,10 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
         int G = (want_ctas + Ns - 1) / Ns;
         Lg = std::min(Lg, std::max(1, (L + G - 1) / G));
     }
+    if (const char* e = getenv("MSM_UNARY_LG")) {  // testing: force the label-group size
+        Lg = std::max(1, std::min(L, atoi(e)));
+        while (Lg > 1 && smem_for(Lg) > 200 * 1024) Lg--;
+    }
     const size_t smem = smem_for(Lg);
     if (smem > 200 * 1024) FAIL("msm_unary_table: control-point patch too large for one CTA's shared memory");
     UnaryArgs a;

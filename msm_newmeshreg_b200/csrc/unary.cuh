@@ -146,6 +146,18 @@ __device__ __forceinline__ double group8_sum(double v) {
     return v;
 }
 
+// The single-item tail and the two-in-flight body of unary_items_uni must give the SAME bits for an item (which of the two
+// handles it depends on the label-group size, i.e. on the shard), so every contraction is spelled out.
+__device__ __forceinline__ void item_coords(const float4& rc, const float2& cc, const float4& m0, const float4& m1, const float4& m2,
+                                            float& x, float& y, float& z) {
+    x = rc.w + (m2.y + fmaf(m0.z, rc.z, fmaf(m0.y, rc.y, m0.x * rc.x)));
+    y = cc.x + (m2.z + fmaf(m1.y, rc.z, fmaf(m1.x, rc.y, m0.w * rc.x)));
+    z = cc.y + (m2.w + fmaf(m2.x, rc.z, fmaf(m1.w, rc.y, m1.z * rc.x)));
+}
+__device__ __forceinline__ float item_value(const float4& f, float tref, float wb, float wc) {
+    return ((f.x - tref) + f.y) + fmaf(wb, f.z, wc * f.w);
+}
+
 // Univariate phase 2 with the number of remaining levels known at compile time and TWO items per thread in flight:
 // the two descents are independent dependency chains (each level waits on a 16-byte table read), so interleaving them
 // hides that latency without needing more resident warps.
@@ -170,9 +182,8 @@ __device__ __forceinline__ void unary_items_uni(const UnaryArgs& a, const float*
             const float2 cc = c2[i];
             const float4* M = reinterpret_cast<const float4*>(sK + l * 12);
             const float4 m0 = M[0], m1 = M[1], m2 = M[2];
-            float x = rc.w + (m2.y + (m0.x * rc.x + m0.y * rc.y + m0.z * rc.z));
-            float y = cc.x + (m2.z + (m0.w * rc.x + m1.x * rc.y + m1.y * rc.z));
-            float z = cc.y + (m2.w + (m1.z * rc.x + m1.w * rc.y + m2.x * rc.z));
+            float x, y, z;
+            item_coords(rc, cc, m0, m1, m2, x, y, z);
             int face = face0;
             if (fminf(x, fminf(y, z)) < 0.f) face = ico_walk(a.hint, face0, x, y, z);
             const int b = face >> hshift;
@@ -181,7 +192,7 @@ __device__ __forceinline__ void unary_items_uni(const UnaryArgs& a, const float*
             for (int lv = 0; lv < NLEV; lv++) ico_descend_level(mtab, nn, x, y, z);
             const float inv = __fdividef(1.0f, x + y + z);
             const float4 f = __ldg(ff + (b * nleaf + ((int)nn - leaf_off)));
-            tb[j0] = ((f.x - tref) + f.y) + ((y * inv) * f.z + (z * inv) * f.w);
+            tb[j0] = item_value(f, tref, y * inv, z * inv);
             continue;
         }
         const int jj[2] = {has0 ? j0 : 0, has1 ? j1 : 0};   // inactive lanes recompute item 0 and do not store
@@ -196,9 +207,7 @@ __device__ __forceinline__ void unary_items_uni(const UnaryArgs& a, const float*
             const float2 cc = c2[i];
             const float4* M = reinterpret_cast<const float4*>(sK + l * 12);
             const float4 m0 = M[0], m1 = M[1], m2 = M[2];
-            al[u] = rc.w + (m2.y + (m0.x * rc.x + m0.y * rc.y + m0.z * rc.z));
-            be[u] = cc.x + (m2.z + (m0.w * rc.x + m1.x * rc.y + m1.y * rc.z));
-            ga[u] = cc.y + (m2.w + (m1.z * rc.x + m1.w * rc.y + m2.x * rc.z));
+            item_coords(rc, cc, m0, m1, m2, al[u], be[u], ga[u]);
             int face = face0;
             if (fminf(al[u], fminf(be[u], ga[u])) < 0.f) face = ico_walk(a.hint, face0, al[u], be[u], ga[u]);
             base[u] = face >> hshift;
@@ -214,7 +223,7 @@ __device__ __forceinline__ void unary_items_uni(const UnaryArgs& a, const float*
             const int leaf = base[u] * nleaf + ((int)n[u] - leaf_off);
             const float inv = __fdividef(1.0f, al[u] + be[u] + ga[u]);
             const float4 f = __ldg(ff + leaf);
-            const float t = ((f.x - tref) + f.y) + ((be[u] * inv) * f.z + (ga[u] * inv) * f.w);
+            const float t = item_value(f, tref, be[u] * inv, ga[u] * inv);
             if (u == 0 ? has0 : has1) tb[jj[u]] = t;
         }
     }

@@ -1,34 +1,25 @@
-"""Scratch GPU debugging / timing breakdown of the end-to-end host path (not a pytest file)."""
-import os
-import sys
-import time
-
+"""scratch: sharded vs single context bits"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
+import problems as pb
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench  # noqa: E402
-from msm_newmeshreg_b200 import host  # noqa: E402
+P = pb.make_problem(5, 3, 1, seed=5, warp=0.3, deform_cp=0.1)
+os.environ.pop("MSM_UNARY_LG", None)
+ctx = pb.gpu_context(P); ctx.build_patches(); U = ctx.unary_table()
+for lg in (19, 7, 3):
+    os.environ["MSM_UNARY_LG"] = str(lg)
+    V = ctx.unary_table()
+    print("single ctx forced Lg", lg, "diff vs natural", (V != U).sum())
+ctx.close()
 
-txyz, ttris = host.icosphere(7)
-cxyz0, ctris = host.icosphere(5)
-mvd = float(np.linalg.norm(cxyz0[ctris[:, 0]] - cxyz0[ctris[:, 1]], axis=1).mean())
-S = bench.Subject(txyz, ttris, 1, 1000, mvd)
-m = host.Model(sgres=7, cpres=5, multivariate=False, dopt="HOCR", threads=1, **bench.PARAMS)
-m.set_data(txyz, ttris, txyz, ttris, S.inp, S.ref)
-m.initialize()
-m.reset_meshspace(S.sxyz)
-cxyz = bench.smooth_warp(cxyz0, 1200, 0.1 * mvd)
-m.reset_cpgrid(cxyz)
-m.setup()
-ctx = m.context()
-ctx.set_timing(1)
-lab = np.random.default_rng(7).integers(0, m.L, m.N).astype(np.int32)
-out = np.empty((m.L, m.T, 8))
-for rep in range(3):
-    t0 = time.perf_counter(); m.reset_meshspace(S.sxyz); t1 = time.perf_counter()
-    m.reset_cpgrid(cxyz); t2 = time.perf_counter()
-    m.setup(); t3 = time.perf_counter()
-    m.triplet_moves(lab, -1, out=out); t4 = time.perf_counter()
-    print(f"rep {rep}: reset_meshspace {1e3 * (t1 - t0):.2f} ms, reset_cpgrid {1e3 * (t2 - t1):.2f}, setup {1e3 * (t3 - t2):.2f} "
-          f"(patches family {ctx.last_kernel_ms('patches'):.2f}, label_rot {ctx.last_kernel_ms('label_rot'):.3f}, unary {ctx.last_kernel_ms('unary'):.3f}), "
-          f"triplet_moves {1e3 * (t4 - t3):.2f} (kernel {ctx.last_kernel_ms('triplet_moves'):.3f})")
+def shard(k0, k1):
+    c = pb.gpu_context(P); c.set_shard(k0, k1); c.build_patches()
+    out = np.zeros_like(U); c.unary_table(out); c.close()
+    return out[:, k0:k1]
+
+for lg in (None, 19, 10, 7, 3, 1):
+    if lg is None: os.environ.pop("MSM_UNARY_LG", None)
+    else: os.environ["MSM_UNARY_LG"] = str(lg)
+    a = shard(0, 214); d = a != U[:, :214]
+    print("shard(0,214) Lg", lg, "diff", d.sum(), "labels", np.unique(np.nonzero(d)[0]))
