@@ -84,7 +84,7 @@ struct msm_ctx {
     // source
     int Vs = 0, Cs = 0, wrows = 0;
     bool multivariate = false;
-    std::vector<double> h_src;
+    PinBuf h_src;            // pinned host copy of the source coordinates (upload staging + exact tie resolution)
     double src_bound = 0.0;  // max |coordinate| of the source mesh (sizes the patch voxel grid)
     DevBuf d_src, d_sxf, d_syf, d_szf, d_sfeat, d_swgt;
 
@@ -122,7 +122,8 @@ struct msm_ctx {
     // outputs / scratch
     DevBuf d_unary, d_scratch, d_scratch2;
     PinBuf h_pin;
-    std::vector<double> h_unary;  // last unary table [L][N] (shard rows) for msm_total_cost
+    std::vector<float> h_unary;   // last unary table, shard rows [L][Ns], for msm_total_cost
+    int h_unary_k0 = 0, h_unary_ns = 0;
     bool have_unary = false;
 };
 
@@ -471,14 +472,23 @@ int msm_set_source(msm_ctx* ctx, const double* xyz, int V, const double* feat, i
 int msm_reset_source(msm_ctx* ctx, const double* xyz) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->Vs <= 0) FAIL("msm_set_source must be called first");
-    // one host pass: keep a copy (exact-tie resolution in msm_build_patches needs the fp64 coordinates) and the
-    // bounding radius; the fp32 SoA copy used by the patch pre-filter is derived on the device
+    // one host pass into a persistent pinned buffer: it is the staging area of the (then truly asynchronous) upload, the
+    // fp64 copy the exact-tie resolution of msm_build_patches reads, and yields the bounding radius of the voxel grid;
+    // the fp32 SoA copy used by the patch pre-filter is derived on the device
     const size_t n3 = (size_t)ctx->Vs * 3;
-    ctx->h_src.resize(n3);
-    double rb = 0.0;
-    for (size_t i = 0; i < n3; i++) { const double v = xyz[i]; ctx->h_src[i] = v; rb = std::max(rb, std::fabs(v)); }
-    ctx->src_bound = rb;
-    if (upload(ctx, ctx->d_src, ctx->h_src.data(), n3)) return 1;
+    CK(cudaStreamSynchronize(ctx->stream));   // a previous upload may still be reading the staging buffer
+    CK(ctx->h_src.ensure(n3 * sizeof(double)));
+    double* hs = ctx->h_src.as<double>();
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    size_t i = 0;
+    for (; i + 4 <= n3; i += 4) {   // four independent max chains
+        const double a = xyz[i], b = xyz[i + 1], c = xyz[i + 2], d = xyz[i + 3];
+        hs[i] = a; hs[i + 1] = b; hs[i + 2] = c; hs[i + 3] = d;
+        m0 = std::max(m0, std::fabs(a)); m1 = std::max(m1, std::fabs(b)); m2 = std::max(m2, std::fabs(c)); m3 = std::max(m3, std::fabs(d));
+    }
+    for (; i < n3; i++) { hs[i] = xyz[i]; m0 = std::max(m0, std::fabs(xyz[i])); }
+    ctx->src_bound = std::max(std::max(m0, m1), std::max(m2, m3));
+    if (upload(ctx, ctx->d_src, hs, n3)) return 1;
     CK(ctx->d_sxf.ensure((size_t)ctx->Vs * 4)); CK(ctx->d_syf.ensure((size_t)ctx->Vs * 4)); CK(ctx->d_szf.ensure((size_t)ctx->Vs * 4));
     k_split_xyz<<<(ctx->Vs + 255) / 256, 256, 0, ctx->stream>>>(ctx->Vs, ctx->d_src.as<double>(), ctx->d_sxf.as<float>(), ctx->d_syf.as<float>(),
                                                                ctx->d_szf.as<float>());
@@ -670,7 +680,7 @@ int msm_build_patches(msm_ctx* ctx) {
         const double RAD = 100.0;
         for (const int2& u : unc) {
             const double* c = &ctx->h_cp[3 * (size_t)u.x];
-            const double* s = &ctx->h_src[3 * (size_t)u.y];
+            const double* s = ctx->h_src.as<double>() + 3 * (size_t)u.y;
             const double X = c[0] - s[0], Y = c[1] - s[1], Z = c[2] - s[2];
             const double norm = std::sqrt(X * X + Y * Y + Z * Z);
             if ((2 * RAD * std::asin(norm / (2 * RAD))) < ctx->par.range * ctx->h_maxsep[u.x]) acc[u.x - ctx->k_begin].push_back(u.y);
@@ -846,13 +856,13 @@ int msm_unary_table(msm_ctx* ctx, double* out) {
     CK(cudaMemcpyAsync(ctx->h_pin.p, ctx->d_unary.p, (size_t)L * Ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const float* h = ctx->h_pin.as<float>();
-    ctx->h_unary.resize((size_t)L * N);
-    for (int l = 0; l < L; l++)
-        for (int r = 0; r < Ns; r++) {
-            const double v = (double)h[(size_t)l * Ns + r];
-            out[(size_t)l * N + ctx->k_begin + r] = v;
-            ctx->h_unary[(size_t)l * N + ctx->k_begin + r] = v;
-        }
+    for (int l = 0; l < L; l++) {
+        double* o = out + (size_t)l * N + ctx->k_begin;
+        const float* hl = h + (size_t)l * Ns;
+        for (int r = 0; r < Ns; r++) o[r] = (double)hl[r];
+    }
+    ctx->h_unary.assign(h, h + (size_t)L * Ns);   // shard rows [L][Ns], as produced (msm_total_cost)
+    ctx->h_unary_k0 = ctx->k_begin; ctx->h_unary_ns = Ns;
     ctx->have_unary = true;
     return 0;
 }
@@ -1142,7 +1152,8 @@ int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]) {
     for (int i = 0; i < ctx->N; i++)
         if (labeling[i] < 0 || labeling[i] >= ctx->L) FAIL("msm_total_cost: labeling out of range");
     if (ctx->have_unary)
-        for (int k = ctx->k_begin; k < ctx->k_end; k++) sums[0] += ctx->h_unary[(size_t)labeling[k] * ctx->N + k];
+        for (int r = 0; r < ctx->h_unary_ns; r++)
+            sums[0] += (double)ctx->h_unary[(size_t)labeling[ctx->h_unary_k0 + r] * ctx->h_unary_ns + r];
     if (ctx->P > 0 && !ctx->par.group) {
         if (check_pairs(ctx)) return 1;
         std::vector<int> q((size_t)ctx->P * 3);

@@ -163,10 +163,10 @@ public:
 
     //---GET DATA---//
     virtual void get_source_data() {  // :394-410 / :458-481 : patches, then the whole unary table in one launch
-        sync_device_state();
-        check(msm_build_patches(ctx));
-        unary_pristine.assign((size_t)m_num_labels * m_num_nodes, 0.0);
-        check(msm_unary_table(ctx, unary_pristine.data()));
+        { HostTimer t("    sync_device_state"); sync_device_state(); }
+        { HostTimer t("    msm_build_patches"); check(msm_build_patches(ctx)); }
+        unary_pristine.resize((size_t)m_num_labels * m_num_nodes);   // every entry is written by msm_unary_table
+        { HostTimer t("    msm_unary_table"); check(msm_unary_table(ctx, unary_pristine.data())); }
         unary_epoch = tables_epoch.load();
     }
 
@@ -234,8 +234,8 @@ protected:
             source_dirty = source_xyz_dirty = false;
         }
         if (source_xyz_dirty) {
-            auto xyz = _SOURCE.coords();
-            check(msm_reset_source(ctx, xyz.data()));
+            HostTimer t("      reset_source upload");
+            check(msm_reset_source(ctx, _SOURCE.coord_data()));   // Point is three packed doubles: no flattening copy
             source_xyz_dirty = false;
         }
         if (grid_dirty) {

@@ -185,23 +185,26 @@ public:
     }
 
     virtual void setupCostFunction() {  // :188-236
+        HostTimer t_all("setupCostFunction");
         resetLabeling();
-        costfct->reset_CPgrid(m_CPgrid);
+        { HostTimer t("  reset_CPgrid"); costfct->reset_CPgrid(m_CPgrid); }
         if (m_iter == 1) {
             costfct->initialize_regulariser();
             costfct->set_octrees(m_inputtree);
         }
         costfct->reset_anatomical();
-        get_rotations(m_ROT);
+        // ROT[k] = rotation(label-grid centre -> CP_k) is only consumed on the host by applyLabeling (:238-243; the cost
+        // function recomputes it on the device): snapshot the grid now, evaluate lazily there — it is ~1/3 of this call
+        m_rot_grid = m_CPgrid; m_rot_stale = true;
         if (m_rescalelabels) m_labels = rescale_sampling_grid();
         else if (m_iter % 2 == 0) m_labels = m_samples;
         else m_labels = m_barycentres;
         m_num_labels = (int)m_labels.size();
         costfct->set_labels(m_labels, m_ROT);
-        costfct->initialize(m_num_nodes, m_num_labels, m_num_pairs, m_num_triplets);
+        { HostTimer t("  initialize"); costfct->initialize(m_num_nodes, m_num_labels, m_num_pairs, m_num_triplets); }
         if (_pairwise) costfct->setPairs(pairs);
         else costfct->setTriplets(triplets);
-        costfct->get_source_data();   // patches + the whole unary table on the GPU
+        { HostTimer t("  get_source_data"); costfct->get_source_data(); }  // patches + the whole unary table on the GPU
         if (optimiser == "MCMC") costfct->set_mcmc_threads(_nthreads);
         m_iter++;
     }
@@ -236,6 +239,7 @@ public:
 
     using DiscreteModel::applyLabeling;
     virtual void applyLabeling() {  // :238-243
+        ensure_rotations();
         for (int i = 0; i < m_CPgrid.nvertices(); i++) m_CPgrid.set_coord(i, m_ROT[i] * m_labels[labeling[i]]);
     }
 
@@ -251,6 +255,16 @@ protected:
     newresampler::Point centre;
     std::vector<newresampler::Point> m_samples, m_barycentres, m_labels;
     std::vector<NEWMAT::Matrix> m_ROT;
+    newresampler::Mesh m_rot_grid;   // control grid as of the last setupCostFunction (what m_ROT refers to)
+    bool m_rot_stale = false;
+    void ensure_rotations() {
+        if (!m_rot_stale) return;
+        newresampler::Mesh current = m_CPgrid;
+        m_CPgrid = m_rot_grid;
+        get_rotations(m_ROT);
+        m_CPgrid = current;
+        m_rot_stale = false;
+    }
     std::shared_ptr<NonLinearSRegDiscreteCostFunction> costfct;
 
     virtual void estimate_pairs() {  // :245-265 edges i<j in vertex / neighbour order

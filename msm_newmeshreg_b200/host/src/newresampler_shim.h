@@ -167,6 +167,8 @@ public:
         resolution_ = resolution;
         build_adjacency();
     }
+    // Point is standard layout {X, Y, Z}: the vertex array IS the flat [nv][3] coordinate array the C ABI takes
+    const double* coord_data() const { static_assert(sizeof(Point) == 3 * sizeof(double), "Point must be three packed doubles"); return V_.empty() ? nullptr : &V_[0].X; }
     std::vector<double> coords() const {
         std::vector<double> o((size_t)nvertices() * 3);
         for (int i = 0; i < nvertices(); i++) { o[3 * i] = V_[i].X; o[3 * i + 1] = V_[i].Y; o[3 * i + 2] = V_[i].Z; }

@@ -2,6 +2,9 @@
 // use: the per-level parameter map `myparam` (src/reg_tools.h:12-13; std::variant replaces boost::variant, with a
 // `boost::get` shim so code written against the reference compiles) and MeshregException (src/reg_tools.h:15-23).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <exception>
 #include <iostream>
 #include <map>
@@ -16,6 +19,15 @@ const T& get(const std::variant<Ts...>& v) { return std::get<T>(v); }
 }  // namespace boost
 
 namespace newmeshreg {
+
+// Diagnostics: with MSM_HOST_TIMING=1 in the environment every HostTimer scope prints its wall time to stderr.
+struct HostTimer {
+    const char* name; double t0 = 0; bool on;
+    static bool enabled() { static const bool e = [] { const char* v = std::getenv("MSM_HOST_TIMING"); return v && std::atoi(v) != 0; }(); return e; }
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit HostTimer(const char* n) : name(n), on(enabled()) { if (on) t0 = now(); }
+    ~HostTimer() { if (on) std::fprintf(stderr, "[msm host] %-28s %8.3f ms\n", name, now() - t0); }
+};
 
 typedef std::map<std::string, std::variant<int, std::string, double, float, bool>> myparam;
 typedef std::pair<std::string, std::variant<int, std::string, double, float, bool>> parameterPair;
