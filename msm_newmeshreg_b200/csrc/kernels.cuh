@@ -304,18 +304,37 @@ __global__ void __launch_bounds__(1024) k_patch_scan(int n, const int* __restric
 // keep full relative precision in fp32 (absolute coordinates at |x|~100 would not resolve an ico7 triangle to 1e-5).
 // Univariate: source values are stored relative to the patch's first sample (Pearson is shift invariant), so the
 // fp32 copy resolves the variation inside the patch rather than the field's absolute level.
+// `vkey` (optional): a spatial key per source vertex (its leaf of the target hierarchy, a nested = space-filling
+// numbering).  The samples of a patch are then PACKED in key order, so that the 32 samples a warp of k_unary works on are
+// neighbours on the sphere: their descents read the same few table lines (the L1 wavefronts of those 16-byte gathers are
+// k_unary's top limiter) and take the same branches.  The public patch list (idx, ascending ids) is not reordered.
 __global__ void __launch_bounds__(128) k_patch_pack(int k_begin, int total, int Cp, int C, int wrows, int V, int univariate,
-                                                    const int* __restrict__ off, const int* __restrict__ idx, const double* __restrict__ src,
-                                                    const double* __restrict__ cp, const double* __restrict__ feat /*[C][V]*/,
-                                                    const float* __restrict__ wgt /*[wrows][V]*/, float* __restrict__ px,
-                                                    float* __restrict__ py, float* __restrict__ pz, float* __restrict__ pa /*[Cp][total]*/,
-                                                    float* __restrict__ pw) {
+                                                    const int* __restrict__ off, const int* __restrict__ idx, const int* __restrict__ vkey,
+                                                    const double* __restrict__ src, const double* __restrict__ cp,
+                                                    const double* __restrict__ feat /*[C][V]*/, const float* __restrict__ wgt /*[wrows][V]*/,
+                                                    float* __restrict__ px, float* __restrict__ py, float* __restrict__ pz,
+                                                    float* __restrict__ pa /*[Cp][total]*/, float* __restrict__ pw) {
+    extern __shared__ int s_key[];
     const int row = blockIdx.x, k = k_begin + row;
     const double ox = cp[3 * k], oy = cp[3 * k + 1], oz = cp[3 * k + 2];
-    const int s_begin = off[row], s_end = off[row + 1];
+    const int s_begin = off[row], s_end = off[row + 1], P = s_end - s_begin;
     const double aref = (univariate && s_end > s_begin) ? feat[idx[s_begin]] : 0.0;
-    for (int s = s_begin + threadIdx.x; s < s_end; s += blockDim.x) {
-        const int i = idx[s];
+    if (vkey) {
+        for (int j = threadIdx.x; j < P; j += blockDim.x) s_key[j] = vkey[idx[s_begin + j]];
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < P; j += blockDim.x) {
+        const int i = idx[s_begin + j];
+        int pos = j;
+        if (vkey) {   // rank of (key, j) among the patch's samples
+            const int kj = s_key[j];
+            pos = 0;
+            for (int t = 0; t < P; t++) {
+                const int kt = s_key[t];
+                pos += (kt < kj || (kt == kj && t < j)) ? 1 : 0;
+            }
+        }
+        const int s = s_begin + pos;
         px[s] = (float)(src[3 * i] - ox); py[s] = (float)(src[3 * i + 1] - oy); pz[s] = (float)(src[3 * i + 2] - oz);
         for (int c = 0; c < Cp; c++) {
             float a = 0.f, w = 0.f;  // padded channels carry zero weight: they drop out of every weighted sum

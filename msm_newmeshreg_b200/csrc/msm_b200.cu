@@ -113,6 +113,8 @@ struct msm_ctx {
     int maxP = 0;
     DevBuf d_counts, d_off, d_idx, d_unc, d_unc_count, d_acc_off, d_acc_idx, d_totmax;
     DevBuf d_px, d_py, d_pz, d_pa, d_pw;
+    DevBuf d_vkey;            // [Vs] spatial sort key of every source vertex (k_vertex_key)
+    bool vkey_valid = false;
     DevBuf d_cell_counts, d_cell_start, d_cell_fill, d_cell_of, d_sorted;  // voxel grid of the source vertices
     DevBuf d_pcx, d_pcy, d_pcz, d_hint_face, d_lab12, d_tref, d_x0;  // k_cp_hint / k_unary_setup outputs
     int pack_cp = 0;
@@ -398,6 +400,7 @@ int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int 
     ctx->have_target = false;
     ctx->face_feat_cq = -1;
     ctx->hint_level = -1;
+    ctx->vkey_valid = false;
     if (!ctx->ico.build(xyz, V, tris, F)) FAIL("msm_set_target: " + ctx->ico.error);
     const IcoHierarchy& H = ctx->ico;
     ctx->Vt = V; ctx->Ft = F; ctx->Ct = feat ? C : 0;
@@ -494,6 +497,7 @@ int msm_reset_source(msm_ctx* ctx, const double* xyz) {
                                                                ctx->d_szf.as<float>());
     KLAUNCH_CHECK();
     ctx->have_patches = false;
+    ctx->vkey_valid = false;
     return 0;
 }
 
@@ -723,8 +727,20 @@ int msm_build_patches(msm_ctx* ctx) {
     CK(ctx->d_px.ensure(tot * 4)); CK(ctx->d_py.ensure(tot * 4)); CK(ctx->d_pz.ensure(tot * 4));
     CK(ctx->d_pa.ensure(tot * 4 * Cp)); CK(ctx->d_pw.ensure(tot * 4 * Cp));
     if (ctx->total > 0) {
-        k_patch_pack<<<Ns, 128, 0, ctx->stream>>>(ctx->k_begin, (int)ctx->total, Cp, ctx->Cs, ctx->wrows, ctx->Vs, ctx->multivariate ? 0 : 1,
-                                                 ctx->d_off.as<int>(), ctx->d_idx.as<int>(), ctx->d_src.as<double>(), ctx->d_cp.as<double>(),
+        // spatial packing order (see k_patch_pack): needs the target hierarchy; skipped for very large patches
+        const int* vkey = nullptr;
+        const char* nosort = getenv("MSM_PATCH_NOSORT");
+        if (ctx->have_target && ctx->maxP <= 8192 && !(nosort && atoi(nosort))) {
+            if (!ctx->vkey_valid) {
+                CK(ctx->d_vkey.ensure((size_t)ctx->Vs * 4));
+                k_vertex_key<<<(ctx->Vs + 127) / 128, 128, 0, ctx->stream>>>(ctx->Vs, ctx->d_src.as<double>(), ico_dev(ctx), ctx->d_vkey.as<int>());
+                KLAUNCH_CHECK();
+                ctx->vkey_valid = true;
+            }
+            vkey = ctx->d_vkey.as<int>();
+        }
+        k_patch_pack<<<Ns, 128, vkey ? (size_t)ctx->maxP * 4 : 0, ctx->stream>>>(ctx->k_begin, (int)ctx->total, Cp, ctx->Cs, ctx->wrows, ctx->Vs, ctx->multivariate ? 0 : 1,
+                                                 ctx->d_off.as<int>(), ctx->d_idx.as<int>(), vkey, ctx->d_src.as<double>(), ctx->d_cp.as<double>(),
                                                  ctx->d_sfeat.as<double>(), ctx->d_swgt.as<float>(), ctx->d_px.as<float>(),
                                                  ctx->d_py.as<float>(), ctx->d_pz.as<float>(), ctx->d_pa.as<float>(), ctx->d_pw.as<float>());
         KLAUNCH_CHECK();

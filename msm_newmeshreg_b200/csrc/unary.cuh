@@ -42,6 +42,16 @@ __device__ __forceinline__ void descend_d(const IcoDev& ico, int nlev, double px
     }
 }
 
+// one thread per source vertex: its leaf of the target hierarchy (canonical nested numbering) — the spatial sort key of
+// k_patch_pack
+__global__ void __launch_bounds__(128) k_vertex_key(int V, const double* __restrict__ src, IcoDev ico, int* __restrict__ key) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int base, n; double al, be, ga;
+    descend_d(ico, ico.depth, src[3 * v], src[3 * v + 1], src[3 * v + 2], base, n, al, be, ga);
+    key[v] = base * ico.nleaf_per_base + (n - ico.leaf_off);
+}
+
 struct UnarySetupArgs {
     int k_begin, L;
     const int* off;                     // [Ns+1]

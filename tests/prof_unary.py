@@ -18,12 +18,15 @@ ctx.set_timing(True)
 ctx.build_patches()
 off, idx = ctx.patches()
 ms = []
+main = []
 for _ in range(reps):
     U = ctx.unary_table()
     ms.append(ctx.last_kernel_ms("unary"))
+    main.append(ctx.last_kernel_ms("unary_main"))
 algb = sum((off[k + 1] - off[k]) * ((48 + 12 * C) * P.L + (16 + 8 * C)) + 8 * P.L for k in range(P.N))
 best = min(ms)
 print(f"C={C} N={P.N} L={P.L} samples={len(idx) * P.L} unary family ms: {['%.4f' % m for m in ms]}  best {best:.4f} ms "
       f"-> {P.N * P.L / best / 1e6:.3f} G evals/s, {algb / best / 1e6:.0f} GB/s algorithmic ({algb / best / 1e6 / 6549.1:.3f} of 6549.1)")
+print("k_unary alone ms:", ["%.4f" % m for m in main], "best %.4f" % min(main))
 print("checksum", float(np.abs(U).sum()), "launches", ctx.launch_count())
 ctx.close()
