@@ -14,8 +14,9 @@ state exceed the 126 MB L2, so successive timed iterations do not find their inp
   value : evaluations / second, inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks.
   e2e   : the same step through the reference-facing host classes (NonLinearSRegDiscreteModel::reset_meshspace ->
           setupCostFunction [patch construction + unary table] -> triplet moves) with pinned HOST buffers in and out.
-  --impl reference : the oracle's CPU restatement of the reference path on the host cores, bounded sample of the same
-          workload (the reference itself needs FSL and cannot be built: SURVEY.md §0.2).
+  --impl reference : THE REFERENCE'S OWN cost-function classes (oracle/_ref/libref_cost.so: its sources compiled in place
+          over stand-ins for the absent FSL libraries) on the host cores, bounded sample of the same workload; falls back
+          to the oracle port (kind "port") only if that library was not built.
 """
 import argparse
 import json
@@ -186,6 +187,72 @@ def oracle_sample(data_level, cp_level, C, rows, threads, seed=1000, steps=1, wa
                 evals_per_s_resident=evals / (tu + tt), evals_per_s_e2e=evals / (tp + tu + tt))
 
 
+def reference_sample(data_level, cp_level, C, rows, threads, seed=1000, steps=1, warmup=0, tables=None):
+    """The same bounded sample through THE REFERENCE'S OWN cost-function classes (oracle/_ref/libref_cost.so = its
+    src/DiscreteCostFunction.cpp, similarities.cc, reg_tools.cpp compiled in place; host/harness.cpp ref_cost_sample).
+    get_source_data + computeUnaryCosts run on ONE thread (the reference's threaded unary loop is a data race, DESIGN.md
+    §1), the re-entrant computeTripletCost on `threads` OpenMP threads as in include/Fusion/Fusion.h:180."""
+    import ctypes as Ct
+    from oracle import pyorc, pyrefcost
+    L_ = pyrefcost.lib()
+    txyz, ttris = pyorc.icosphere(data_level)
+    cxyz0, ctris = pyorc.icosphere(cp_level)
+    maxsep, mvdmax, mvd = pyorc.spacings(cxyz0, ctris)
+    S = Subject(txyz, ttris, C, seed, mvd)
+    samples, bary, centre = pyorc.label_grid(cp_level + 2, 0.5 * mvdmax)
+    cxyz = smooth_warp(cxyz0, seed + 200, 0.1 * mvd)
+    trip = pyorc.triplets(cxyz0, ctris)
+    N, L, T = len(cxyz), len(bary), len(trip)
+    rows = min(rows, N)
+    ntrip = max(1, T * rows // N)
+    lab = np.random.default_rng(7).integers(0, L, N).astype(np.int32)
+    d = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    i = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    dp, ip = Ct.POINTER(Ct.c_double), Ct.POINTER(Ct.c_int)
+    A = dict(txyz=d(txyz), ttris=i(ttris), sxyz=d(S.sxyz), inp=d(S.inp), ref=d(S.ref), cp0=d(cxyz0), cp=d(cxyz), ctris=i(ctris),
+             maxsep=d(maxsep), labels=d(bary), trip=i(trip[:ntrip]), lab=i(lab))
+    P = {k: Ct.c_double(PARAMS[k]) for k in ("lam", "rexp", "mu", "kappa", "k_exp", "rng")}
+    sec = np.zeros(3)
+    times = {"patches": [], "unary": [], "triplet": []}
+    u_out = m_out = None
+    if tables is not None:   # tests: hand the evaluated sample back
+        tables["unary"] = np.zeros((L, rows)); tables["moves"] = np.zeros((L, ntrip, 8)); tables["labeling"] = lab
+        u_out, m_out = tables["unary"].ctypes.data_as(dp), tables["moves"].ctypes.data_as(dp)
+    for it in range(warmup + steps):
+        st = L_.ref_cost_sample(A["txyz"].ctypes.data_as(dp), len(txyz), A["ttris"].ctypes.data_as(ip), len(ttris), A["sxyz"].ctypes.data_as(dp),
+                                A["inp"].ctypes.data_as(dp), A["ref"].ctypes.data_as(dp), C, int(C > 1), A["cp0"].ctypes.data_as(dp),
+                                A["cp"].ctypes.data_as(dp), N, A["ctris"].ctypes.data_as(ip), len(ctris), A["maxsep"].ctypes.data_as(dp),
+                                Ct.c_double(mvdmax), A["labels"].ctypes.data_as(dp), L, P["lam"], P["rexp"], P["mu"], P["kappa"], P["k_exp"],
+                                P["rng"], int(PARAMS["simmeasure"]), int(PARAMS["rmode"]), rows, ntrip, A["trip"].ctypes.data_as(ip),
+                                A["lab"].ctypes.data_as(ip), threads, u_out, m_out, sec.ctypes.data_as(dp))
+        if st != 0:
+            raise RuntimeError(L_.msmhost_last_error().decode())
+        if it >= warmup:
+            times["patches"].append(sec[0]); times["unary"].append(sec[1]); times["triplet"].append(sec[2])
+    tp, tu, tt = (float(np.mean(times[k])) for k in ("patches", "unary", "triplet"))
+    evals = rows * L + L * ntrip * 8
+    return dict(evals=evals, rows=rows, N=N, L=L, T=T, ntrip=ntrip, t_patches=tp, t_unary=tu, t_triplet=tt,
+                evals_per_s_resident=evals / (tu + tt), evals_per_s_e2e=evals / (tp + tu + tt))
+
+
+def cpu_sample(data_level, cp_level, C, rows, threads, steps=1, warmup=0):
+    """CPU arm: the reference's own classes when oracle/_ref/libref_cost.so was built (kind "reference"), else the
+    oracle port (kind "port").  Returns (result dict, kind, description of the sample)."""
+    from oracle import pyrefcost
+    if pyrefcost.available():
+        r = reference_sample(data_level, cp_level, C, rows, threads, steps=steps, warmup=warmup)
+        kind = "reference"
+        how = (f"reference's own DiscreteCostFunction classes compiled in place (oracle/_ref/libref_cost.so): get_source_data + "
+               f"computeUnaryCosts on 1 thread (more is a data race in the reference), computeTripletCost on {threads} threads")
+    else:
+        r = oracle_sample(data_level, cp_level, C, rows, threads, steps=steps, warmup=warmup)
+        kind = "port"
+        how = f"oracle port (oracle/_ref/libref_cost.so not built): patch construction 1 thread as in the reference, tables {threads} threads"
+    sample = (f"{r['rows']} of {r['N']} control points + {r['ntrip']} of {r['T']} triplets x {r['L']} labels x 8 moves; {how}; "
+              f"patches {r['t_patches']:.2f}s, unary {r['t_unary']:.2f}s, triplets {r['t_triplet']:.3f}s")
+    return r, kind, sample
+
+
 # ---------------------------------------------------------------------------------------------- CP-sharded mode
 def bench_cp_sharded(args, rank, world, local, C, metric, unit):
     """ONE HCP-scale registration (ico7 / ico5): control points and triplets split into contiguous ranges over the GPUs
@@ -292,14 +359,12 @@ def main():
         except Exception as e:  # prebuilt oracle/liborc.so travels with the snapshot
             print(f"# oracle rebuild skipped: {e}", file=sys.stderr)
         threads = os.cpu_count() or 1
-        r = oracle_sample(args.data_level, args.cp_level, C, args.cpu_rows, threads, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+        r, kind, sample = cpu_sample(args.data_level, args.cp_level, C, args.cpu_rows, threads, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
         v = r["evals_per_s_e2e"]
-        sample = (f"{r['rows']} of {r['N']} control points (patch construction 1 thread as in the reference, unary {threads} threads) + "
-                  f"{r['ntrip']} of {r['T']} triplets x {r['L']} labels x 8 moves; oracle port (reference needs FSL)")
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * (r["t_patches"] + r["t_unary"] + r["t_triplet"]), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload, "sample": sample},
-                "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port", "sample": sample,
+                "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": kind, "sample": sample,
                                  "value_tables_only": r["evals_per_s_resident"], "t_patches_s": r["t_patches"], "t_unary_s": r["t_unary"],
                                  "t_triplet_s": r["t_triplet"]},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -463,10 +528,8 @@ def main():
         if world == 1:
             try:
                 threads = os.cpu_count() or 1
-                r = oracle_sample(args.data_level, args.cp_level, C, args.cpu_rows, threads, steps=1, warmup=0)
-                line["cpu_baseline"] = {"value": r["evals_per_s_e2e"], "unit": unit, "cores": threads, "kind": "port",
-                                        "sample": f"{r['rows']} of {r['N']} control points + {r['ntrip']} of {r['T']} triplets x {r['L']} labels x 8 "
-                                                  f"(patches {r['t_patches']:.2f}s 1 thread, unary {r['t_unary']:.2f}s, triplets {r['t_triplet']:.2f}s)",
+                r, kind, sample = cpu_sample(args.data_level, args.cp_level, C, args.cpu_rows, threads, steps=1, warmup=0)
+                line["cpu_baseline"] = {"value": r["evals_per_s_e2e"], "unit": unit, "cores": threads, "kind": kind, "sample": sample,
                                         "value_tables_only": r["evals_per_s_resident"]}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}

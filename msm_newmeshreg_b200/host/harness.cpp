@@ -367,6 +367,91 @@ int ref_model_patches(void* h, int* sizes, int* idx) {
         }
     });
 }
+// Bounded sample of ONE outer iteration through the reference's own cost-function classes (bench.py --impl reference /
+// cpu_baseline): the model cannot evaluate a subset of control points and a full HCP-scale set-up is ~1 minute of
+// single-threaded brute-force patch search, so the cost functions are driven directly, in the order setupCostFunction
+// uses (src/DiscreteModel.cpp:188-236), on
+//   * the first `rows` control points for get_source_data + computeUnaryCosts (ONE thread: the reference's threaded
+//     unary loop is racy), and
+//   * `ntrip` triplets for the 8 fusion-move costs of every proposal label (computeTripletCost is re-entrant: `threads`
+//     OpenMP threads, as include/Fusion/Fusion.h:180 does).
+// seconds[3] = get_source_data, computeUnaryCosts, triplet moves.
+int ref_cost_sample(const double* txyz, int Vt, const int* ttris, int Ft, const double* sxyz, const double* input, const double* ref, int C,
+                    int multivariate, const double* cp0_xyz, const double* cp_xyz, int N, const int* ctris, int Tc, const double* maxsep,
+                    double mvdmax, const double* labels, int L, double lambda, double rexp, double mu, double kappa, double kexp, double range,
+                    int simmeasure, int rmode, int rows, int ntrip, const int* triplets, const int* labeling, int threads, double* unary_out,
+                    double* moves_out, double* seconds) {
+    return guard([&] {
+        myparam P = default_parameters();
+        P["lambda"] = (float)lambda; P["exponent"] = (float)rexp; P["shearmodulus"] = (float)mu; P["bulkmodulus"] = (float)kappa;
+        P["kexponent"] = (float)kexp; P["range"] = (float)range; P["simmeasure"] = simmeasure; P["regularisermode"] = rmode;
+        P["numthreads"] = 1;
+        const newresampler::Mesh target = mesh_from(txyz, Vt, ttris, Ft);
+        const newresampler::Mesh source = mesh_from(sxyz, Vt, ttris, Ft);
+        auto feat = make_features(input, Vt, ref, Vt, C);
+        std::vector<newresampler::Point> lab(L);
+        for (int i = 0; i < L; i++) lab[i] = newresampler::Point(labels[3 * i], labels[3 * i + 1], labels[3 * i + 2]);
+        auto rotations = [&](const double* cp, int n) {   // src/DiscreteModel.cpp:284-294 (labels[0] = label-grid centre)
+            std::vector<NEWMAT::Matrix> R(n);
+            for (int k = 0; k < n; k++) R[k] = estimate_rotation_matrix(lab[0], newresampler::Point(cp[3 * k], cp[3 * k + 1], cp[3 * k + 2]));
+            return R;
+        };
+        NEWMAT::Matrix ones; ones.ReSize(1, Vt); ones = 1;
+        seconds[0] = seconds[1] = seconds[2] = 0.0;
+        if (rows > 0) {
+            std::shared_ptr<NonLinearSRegDiscreteCostFunction> cf;
+            if (multivariate) cf = std::make_shared<MultivariateNonLinearSRegDiscreteCostFunction>();
+            else cf = std::make_shared<UnivariateNonLinearSRegDiscreteCostFunction>();
+            cf->set_parameters(P);
+            const newresampler::Mesh grid = mesh_from(cp_xyz, rows, nullptr, 0);   // the sampled control points, vertices only
+            cf->set_meshes(target, source, grid);
+            cf->set_featurespace(feat);
+            NEWMAT::ColumnVector ms(rows);
+            for (int k = 0; k < rows; k++) ms(k + 1) = maxsep[k];
+            cf->set_spacings(ms, mvdmax);
+            std::shared_ptr<newresampler::Octree> tree = std::make_shared<newresampler::Octree>(target);   // :88
+            cf->set_octrees(tree);
+            cf->set_dataaffintyweighting(ones);                                   // src/mesh_registration.cpp:330-335
+            cf->set_labels(lab, rotations(cp_xyz, rows));
+            cf->initialize(rows, L, 0, 0);
+            double t0 = omp_get_wtime();
+            cf->get_source_data();
+            double t1 = omp_get_wtime();
+            cf->computeUnaryCosts();
+            double t2 = omp_get_wtime();
+            seconds[0] = t1 - t0; seconds[1] = t2 - t1;
+            if (unary_out) std::memcpy(unary_out, cf->getUnaryCosts(), sizeof(double) * (size_t)rows * L);
+        }
+        if (ntrip > 0) {
+            UnivariateNonLinearSRegDiscreteCostFunction cf;
+            cf.set_parameters(P);
+            const newresampler::Mesh grid0 = mesh_from(cp0_xyz, N, ctris, Tc);
+            cf.set_meshes(target, target, grid0);                                 // _ORIG = the undeformed template (:175-177)
+            cf.set_featurespace(feat);
+            cf.reset_CPgrid(mesh_from(cp_xyz, N, ctris, Tc));
+            cf.set_initial_angles(grid0.get_face_angles());
+            NEWMAT::ColumnVector ms(N);
+            for (int k = 0; k < N; k++) ms(k + 1) = maxsep[k];
+            cf.set_spacings(ms, mvdmax);
+            cf.set_labels(lab, rotations(cp_xyz, N));
+            std::vector<int> trip(triplets, triplets + 3 * (size_t)ntrip);
+            cf.initialize(N, L, 0, ntrip);
+            cf.setTriplets(trip.data());
+            double t0 = omp_get_wtime();
+#pragma omp parallel for collapse(2) num_threads(threads)
+            for (int a = 0; a < L; a++)
+                for (int t = 0; t < ntrip; t++) {
+                    const int cur[3] = {labeling[trip[3 * t]], labeling[trip[3 * t + 1]], labeling[trip[3 * t + 2]]};
+                    for (int m = 0; m < 8; m++) {
+                        const double v = cf.computeTripletCost(t, (m & 4) ? a : cur[0], (m & 2) ? a : cur[1], (m & 1) ? a : cur[2]);
+                        if (moves_out) moves_out[((size_t)a * ntrip + t) * 8 + m] = v;
+                    }
+                }
+            seconds[2] = omp_get_wtime() - t0;
+        }
+    });
+}
+
 void* ref_gc_create() { return new GroupBox(); }
 void ref_gc_destroy(void* h) { delete (GroupBox*)h; }
 int ref_gc_set(void* h, double lambda, double rexp, double mu, double kappa, int S, const double* cp_xyz /*S*N*3*/, int N, const int* cp_tris,

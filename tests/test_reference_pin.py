@@ -201,3 +201,29 @@ def test_reference_optimisers_on_reference_costs_equal_oracle_tables():
         lab_orc, e_orc = pyref.fusion_tables(cf.unary_costs(), P.triplets, cf.triplet_table(), threads=2)
         assert np.array_equal(lab_ref, lab_orc) and abs(e_ref - e_orc) <= 1e-9 * abs(e_orc)
     m.close()
+
+
+def test_bench_reference_sample_equals_oracle_sample():
+    """bench.py's CPU arm drives the reference's cost functions directly on a bounded sample (host/harness.cpp
+    ref_cost_sample): the sample must be the same numbers the oracle port produces for those control points / triplets."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    tabs = {}
+    r = bench.reference_sample(4, 2, 1, rows=40, threads=2, tables=tabs)
+    txyz, ttris = pyorc.icosphere(4); cxyz0, ctris = pyorc.icosphere(2)
+    maxsep, mvdmax, mvd = pyorc.spacings(cxyz0, ctris)
+    S = bench.Subject(txyz, ttris, 1, 1000, mvd)
+    samples, bary, centre = pyorc.label_grid(4, 0.5 * mvdmax)
+    cxyz = pb.smooth_warp(cxyz0, 1200, 0.1 * mvd)
+    trip = pyorc.triplets(cxyz0, ctris)
+    cf = pyorc.CostFunction(); cf.set_params(threads=2, **bench.PARAMS)
+    cf.set_meshes(txyz, ttris, S.sxyz, cxyz0, ctris); cf.reset_cpgrid(cxyz); cf.set_orig(cxyz0)
+    cf.set_features(S.ref, S.inp, False); cf.set_spacings(maxsep, mvdmax)
+    cf.set_labels(bary, pyorc.rotations(centre, cxyz)); cf.set_triplets(trip)
+    cf.get_source_data(0, 40)
+    assert np.abs(tabs["unary"] - cf.unary_costs(0, 40)[:, :40]).max() < 1e-12
+    lab, L, nt = tabs["labeling"], r["L"], r["ntrip"]
+    q = np.array([[t, a if c & 4 else lab[trip[t, 0]], a if c & 2 else lab[trip[t, 1]], a if c & 1 else lab[trip[t, 2]]]
+                  for a in range(L) for t in range(nt) for c in range(8)], np.int32)
+    assert pb.rel_err(tabs["moves"].ravel(), cf.triplet_costs(q), 1e-9).max() < 1e-9
