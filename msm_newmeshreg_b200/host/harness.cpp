@@ -52,6 +52,9 @@ std::vector<int> faces_of(const newresampler::Mesh& m) {
     for (int t = 0; t < m.ntriangles(); t++) for (int j = 0; j < 3; j++) o[3 * t + j] = m.get_triangle_vertexID(t, j);
     return o;
 }
+void assign_coords(newresampler::Mesh& m, const double* xyz) {
+    for (int i = 0; i < m.nvertices(); i++) m.set_coord(i, newresampler::Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+}
 // The reference's featurespace only has file-name constructors (src/featurespace.h:14-15; featurespace.cc needs FSL
 // I/O and is not compiled): oracle/ref_cost_ext.cpp defines them to take their matrices from this registry instead.
 }  // namespace
@@ -93,6 +96,7 @@ newresampler::Mesh mesh_from(const double* xyz, int nv, const int* tris, int nf)
 }
 std::vector<double> coords_of(const newresampler::Mesh& m) { return m.coords(); }
 std::vector<int> faces_of(const newresampler::Mesh& m) { return m.faces(); }
+void assign_coords(newresampler::Mesh& m, const double* xyz) { m.set_coords(xyz); }   // one bulk copy
 std::shared_ptr<featurespace> make_features(const double* input, int Vin, const double* ref, int Vref, int dim) {
     return std::make_shared<featurespace>(input, Vin, ref, Vref, dim);
 }
@@ -210,7 +214,7 @@ int msmhost_model_sizes(void* h, int* N, int* L, int* P, int* T) {
 int msmhost_model_reset_meshspace(void* h, const double* sxyz) {  // src/mesh_registration.cpp:336
     auto* b = (ModelBox*)h;
     return guard([&] {
-        for (int i = 0; i < b->source.nvertices(); i++) b->source.set_coord(i, newresampler::Point(sxyz[3 * i], sxyz[3 * i + 1], sxyz[3 * i + 2]));
+        assign_coords(b->source, sxyz);
         b->model->reset_meshspace(b->source);
     });
 }
@@ -218,7 +222,7 @@ int msmhost_model_reset_cpgrid(void* h, const double* cxyz) {  // :393
     auto* b = (ModelBox*)h;
     return guard([&] {
         newresampler::Mesh g = b->model->get_CPgrid();
-        for (int i = 0; i < g.nvertices(); i++) g.set_coord(i, newresampler::Point(cxyz[3 * i], cxyz[3 * i + 1], cxyz[3 * i + 2]));
+        assign_coords(g, cxyz);
         b->model->reset_CPgrid(g);
     });
 }
@@ -512,7 +516,7 @@ int ref_run_discrete_opt(void* h, int iters, int threads, double* source_xyz, in
     const int st = guard([&] {
         const std::string dopt = boost::get<std::string>(b->params.find("dOPT")->second);
         newresampler::Mesh source = b->source;
-        for (int i = 0; i < source.nvertices(); i++) source.set_coord(i, newresampler::Point(source_xyz[3 * i], source_xyz[3 * i + 1], source_xyz[3 * i + 2]));
+        assign_coords(source, source_xyz);
         double energy = 0.0, newenergy = 0.0;
         for (int iter = 1; iter <= iters; iter++) {
             double t0 = omp_get_wtime();

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -125,14 +126,20 @@ private:
 
 class Mesh {  // A7 (container + adjacency; no I/O: on-disk formats stay outside the hot path)
 public:
-    int nvertices() const { return (int)V_.size(); }
+    int nvertices() const { return (int)V().size(); }
     int ntriangles() const { return (int)topo_->F.size(); }
-    const Point& get_coord(int i) const { return V_[i]; }
-    void set_coord(int i, const Point& p) { V_[i] = p; }
+    const Point& get_coord(int i) const { return V()[i]; }
+    void set_coord(int i, const Point& p) { Vw()[i] = p; }
+    // all vertices at once from a flat [nv][3] array: one bulk copy into storage of its own (other copies keep theirs)
+    void set_coords(const double* xyz) {
+        auto n = std::make_shared<std::vector<Point>>(V().size());
+        if (!n->empty()) std::memcpy(static_cast<void*>(n->data()), xyz, n->size() * sizeof(Point));
+        V_ = std::move(n);
+    }
     int get_triangle_vertexID(int t, int j) const { return topo_->F[t][j]; }
-    Point get_triangle_vertex(int t, int j) const { return V_[topo_->F[t][j]]; }
+    Point get_triangle_vertex(int t, int j) const { return V()[topo_->F[t][j]]; }
     Triangle get_triangle(int t) const {
-        Triangle T(V_[topo_->F[t][0]], V_[topo_->F[t][1]], V_[topo_->F[t][2]], t);
+        Triangle T(V()[topo_->F[t][0]], V()[topo_->F[t][1]], V()[topo_->F[t][2]], t);
         for (int j = 0; j < 3; j++) T.set_vertex_no(j, topo_->F[t][j]);
         return T;
     }
@@ -144,12 +151,12 @@ public:
     int get_resolution() const { return resolution_; }
     double calculate_MaxVD() const {
         double mx = 0;
-        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) mx = std::max(mx, (V_[i] - V_[j]).norm());
+        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) mx = std::max(mx, (V()[i] - V()[j]).norm());
         return mx;
     }
     double calculate_MeanVD() const {
         double s = 0; long n = 0;
-        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) { s += (V_[i] - V_[j]).norm(); n++; }
+        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) { s += (V()[i] - V()[j]).norm(); n++; }
         return n ? s / n : 0;
     }
     std::vector<std::vector<double>> get_face_angles() const {
@@ -160,18 +167,18 @@ public:
     // construction
     void set(const double* xyz, int nv, const int* tris, int nf, int resolution = -1) {
         topo_ = std::make_shared<Topo>();  // never mutate a topology another copy may share
-        V_.resize(nv);
-        for (int i = 0; i < nv; i++) V_[i] = Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+        V_ = std::make_shared<std::vector<Point>>(nv);
+        for (int i = 0; i < nv; i++) (*V_)[i] = Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
         topo_->F.resize(nf);
         for (int t = 0; t < nf; t++) topo_->F[t] = {tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]};
         resolution_ = resolution;
         build_adjacency();
     }
     // Point is standard layout {X, Y, Z}: the vertex array IS the flat [nv][3] coordinate array the C ABI takes
-    const double* coord_data() const { static_assert(sizeof(Point) == 3 * sizeof(double), "Point must be three packed doubles"); return V_.empty() ? nullptr : &V_[0].X; }
+    const double* coord_data() const { static_assert(sizeof(Point) == 3 * sizeof(double), "Point must be three packed doubles"); return V().empty() ? nullptr : &V()[0].X; }
     std::vector<double> coords() const {
         std::vector<double> o((size_t)nvertices() * 3);
-        for (int i = 0; i < nvertices(); i++) { o[3 * i] = V_[i].X; o[3 * i + 1] = V_[i].Y; o[3 * i + 2] = V_[i].Z; }
+        for (int i = 0; i < nvertices(); i++) { o[3 * i] = V()[i].X; o[3 * i + 1] = V()[i].Y; o[3 * i + 2] = V()[i].Z; }
         return o;
     }
     std::vector<int> faces() const {
@@ -181,7 +188,7 @@ public:
     }
     // adjacency order: faces ascending; neighbours by first appearance over those faces
     void build_adjacency() {
-        topo_->nbr.assign(V_.size(), {}); topo_->vtri.assign(V_.size(), {});
+        topo_->nbr.assign(V().size(), {}); topo_->vtri.assign(V().size(), {});
         for (int t = 0; t < ntriangles(); t++) for (int j = 0; j < 3; j++) topo_->vtri[topo_->F[t][j]].push_back(t);
         for (int v = 0; v < nvertices(); v++)
             for (int t : topo_->vtri[v])
@@ -190,8 +197,16 @@ public:
                     if (u != v && std::find(topo_->nbr[v].begin(), topo_->nbr[v].end(), u) == topo_->nbr[v].end()) topo_->nbr[v].push_back(u);
                 }
     }
-    std::vector<Point> V_;
 private:
+    // Coordinates are copy-on-write: the drivers copy meshes freely (reset_meshspace / reset_CPgrid / get_CPgrid take and
+    // return meshes by value, src/DiscreteModel.h:108-119), a copy costs nothing until one side moves a vertex.  (Not for
+    // concurrent mutation of copies of one mesh — nothing in the path does that.)
+    std::shared_ptr<std::vector<Point>> V_ = std::make_shared<std::vector<Point>>();
+    const std::vector<Point>& V() const { return *V_; }
+    std::vector<Point>& Vw() {
+        if (V_.use_count() > 1) V_ = std::make_shared<std::vector<Point>>(*V_);
+        return *V_;
+    }
     // topology is immutable once set and shared between copies: the drivers copy meshes freely
     // (reset_meshspace / reset_CPgrid take meshes by value semantics), only coordinates ever change
     struct Topo {

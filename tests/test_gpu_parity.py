@@ -380,3 +380,32 @@ def test_full_size_c3_properties(built):
             q.append([t, 4 if combo & 4 else a, 4 if combo & 2 else b, 4 if combo & 1 else c])
     _check(mv[ts].ravel(), cf.triplet_costs(np.array(q, np.int32)), 1e-3 * pb.DEFAULT_PARAMS["lam"], "C3 moves", tol=1e-9)
     ctx.close()
+
+
+def test_unary_bits_do_not_depend_on_label_group_size(built, monkeypatch):
+    """The per-item arithmetic is written so that an item gives the same bits wherever it is processed (two-in-flight body,
+    single-item tail, any label-group size): forcing the group size must not change one bit of the table."""
+    P = pb.make_problem(5, 3, 1, seed=5, warp=0.3, deform_cp=0.1)
+    ctx = pb.gpu_context(P); ctx.build_patches()
+    monkeypatch.delenv("MSM_UNARY_LG", raising=False)
+    U = ctx.unary_table()
+    for lg in (19, 10, 7, 3, 1):
+        monkeypatch.setenv("MSM_UNARY_LG", str(lg))
+        assert np.array_equal(ctx.unary_table(), U), f"label-group size {lg}"
+    ctx.close()
+
+
+@pytest.mark.parametrize("C", [1, 4])
+def test_spatial_packing_order_only_reorders_sums(built, monkeypatch, C):
+    """k_patch_pack packs samples in target-leaf order (cache locality); the public patch lists stay ascending and the
+    table changes only by the rounding of re-ordered sums."""
+    P = pb.make_problem(5, 3, C, seed=6, warp=0.3, deform_cp=0.1)
+    tabs, lists = [], []
+    for nosort in ("1", "0"):
+        monkeypatch.setenv("MSM_PATCH_NOSORT", nosort)
+        ctx = pb.gpu_context(P); ctx.build_patches()
+        tabs.append(ctx.unary_table()); lists.append(ctx.patches()); ctx.close()
+    assert np.array_equal(lists[0][0], lists[1][0]) and np.array_equal(lists[0][1], lists[1][1])
+    assert pb.rel_err(tabs[1], tabs[0], 1e-2).max() < 2e-6
+    cf = pb.oracle_costfunction(P); cf.get_source_data()
+    assert pb.rel_err(tabs[1], cf.unary_costs(), 1e-2).max() < 1e-5
