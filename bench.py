@@ -283,12 +283,50 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
     d_unary = torch.empty((L, k1 - k0), dtype=torch.float32, device="cuda")
     d_moves = torch.empty((L, (t1 - t0) * 8), dtype=torch.float32, device="cuda")
 
-    def step():
+    def step_nccl():
         ctx.unary_table_dev(d_unary.data_ptr())
         ctx.triplet_moves_range_dev(lab_dev.data_ptr(), -1, t0, t1, d_moves.data_ptr())
         U = sharding.allgather_label_major(d_unary, N)
         M = sharding.allgather_label_major(d_moves, T, unit=8)
         return U, M
+
+    # Fused exchange: the kernels store every finished entry straight into the full table of EVERY rank through
+    # symmetric-memory peer mappings (NVLink stores) — no all-gather, no re-layout; one device-side barrier per step.
+    # (A consumer that reads the tables between steps needs a second barrier, or two table sets, before the next step
+    # may overwrite them; the bench only reads after the last step.)
+    exchange, why = args.cp_exchange, ""
+    full_u = full_m = hdl = None
+    if exchange == "p2p":
+        try:
+            if world > 1:
+                import torch.distributed._symmetric_memory as symm_mem
+                full_u = symm_mem.empty(L * N, dtype=torch.float32, device=f"cuda:{local}")
+                full_m = symm_mem.empty(L * T * 8, dtype=torch.float32, device=f"cuda:{local}")
+                hdl = symm_mem.rendezvous(full_u, dist.group.WORLD)
+                hdl_m = symm_mem.rendezvous(full_m, dist.group.WORLD)
+                peer_u, peer_m = [int(p) for p in hdl.buffer_ptrs], [int(p) for p in hdl_m.buffer_ptrs]
+            else:
+                full_u = torch.empty(L * N, dtype=torch.float32, device="cuda")
+                full_m = torch.empty(L * T * 8, dtype=torch.float32, device="cuda")
+                peer_u, peer_m = [full_u.data_ptr()], [full_m.data_ptr()]
+        except Exception as e:   # no symmetric memory on this box: fall back to the NCCL gather
+            exchange, why = "nccl", f" (p2p unavailable: {type(e).__name__}: {e})"
+
+    def step_p2p():
+        ctx.unary_table_peers(peer_u)
+        ctx.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, peer_m)
+        if hdl is not None:
+            hdl.barrier(channel=0)
+        return full_u.view(L, N), full_m.view(L, T * 8)
+
+    if exchange == "p2p":   # the two exchanges must produce the same tables
+        Un, Mn = step_nccl()
+        Up, Mp = step_p2p()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        assert torch.equal(Un, Up) and torch.equal(Mn.reshape(L, -1), Mp), "fused exchange differs from the NCCL gather"
+    step = step_p2p if exchange == "p2p" else step_nccl
 
     def sync_all():
         torch.cuda.synchronize()
@@ -317,8 +355,10 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (unary) / f64 (triplet)", "data": "synthetic",
             "config": {"workload": f"C3 CP-sharded: ONE ico{args.data_level}/ico{args.cp_level} registration, control points and triplets "
-                                   f"split over {world} GPU(s), unary [L][N] and fusion-move [L][T][8] tables gathered with NCCL all_gather",
-                       "N": N, "L": L, "T": T, "gathered_bytes_per_step": 4 * (L * N + L * T * 8),
+                                   f"split over {world} GPU(s), unary [L][N] and fusion-move [L][T][8] tables "
+                                   + ("written by the kernels straight into every rank's table over NVLink peer mappings (fused exchange, "
+                                      "one device-side barrier per step)" if exchange == "p2p" else "gathered with NCCL all_gather" + why),
+                       "exchange": exchange, "N": N, "L": L, "T": T, "gathered_bytes_per_step": 4 * (L * N + L * T * 8),
                        "l2": "single subject: inputs are L2 resident between steps (mode used to show the sharded path, not the headline)"},
             "gpu_launches": int(ctx.launch_count() - launches0), "checksum": checksum}))
     if world > 1:
@@ -340,6 +380,9 @@ def main():
     ap.add_argument("--mode", default="subjects", choices=["subjects", "cp"],
                     help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
                          "and triplets sharded over the GPUs, table slices all-gathered with NCCL (strong scaling)")
+    ap.add_argument("--cp-exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="--mode cp: p2p = kernels store into every rank's table through symmetric-memory peer mappings "
+                         "(fused exchange); nccl = all_gather_into_tensor + re-layout")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

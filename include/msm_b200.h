@@ -117,6 +117,16 @@ int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float*
 /* Multi-GPU: the same for the triplet shard [t0,t1): d_out float[L or 1][t1-t0][8]. */
 int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, float* d_out);
 
+/* Fused exchange for control-point / triplet sharding (replaces "kernel, then all-gather, then
+ * re-layout"): the kernels store every finished entry straight into the FULL table of EVERY rank.  peer_tables[r]
+ * (r < world <= 16) is a device pointer, valid on this context's GPU, to rank r's buffer — CUDA IPC or symmetric-memory
+ * mappings over NVLink; peer_tables[own rank] is the local buffer.
+ *   msm_unary_table_peers        : float[L][N], rows [k_begin,k_end) of this context's shard (msm_set_shard)
+ *   msm_triplet_moves_range_peers: float[L or 1][T][8], triplets [t0,t1)
+ * Launched on the context stream; the caller makes the ranks wait for each other afterwards (a barrier on the stream). */
+int msm_unary_table_peers(msm_ctx* ctx, void* const* peer_tables, int world);
+int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, void* const* peer_tables, int world);
+
 /* computePairwiseCosts (src/DiscreteCostFunction.cpp:256-304): out float[P][L][L] in the reference layout. */
 int msm_pair_table(msm_ctx* ctx, float* out);
 int msm_pair_table_dev(msm_ctx* ctx, float* d_out);

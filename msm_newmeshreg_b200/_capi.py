@@ -27,7 +27,7 @@ EXPORTS = [
     "msm_set_target", "msm_set_source", "msm_reset_source", "msm_set_cpgrid", "msm_reset_cpgrid", "msm_set_shard", "msm_set_labels",
     "msm_set_pairs", "msm_set_triplets", "msm_set_group", "msm_build_patches", "msm_patch_count", "msm_get_patches",
     "msm_unary_table", "msm_unary_table_dev", "msm_triplet_costs", "msm_triplet_table", "msm_triplet_table_dev", "msm_triplet_moves",
-    "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count",
+    "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count",
     "msm_set_timing", "msm_last_kernel_ms", "msm_timing_collect", "msm_set_group_patches", "msm_group_pair_costs",
     "msm_group_pair_moves", "msm_mesh_interpolate",
 ]
@@ -226,6 +226,20 @@ class Context:
 
     def triplet_moves_range_dev(self, labeling_dev_ptr, alpha, t0, t1, out_dev_ptr):
         self._ck(lib().msm_triplet_moves_range_dev(self._h, C.c_void_p(labeling_dev_ptr), int(alpha), int(t0), int(t1), C.c_void_p(out_dev_ptr)))
+
+    # fused exchange (control-point / triplet sharding): peer_ptrs = device pointers to every rank's FULL table
+    @staticmethod
+    def _peer_array(peer_ptrs):
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        return arr, len(peer_ptrs)
+
+    def unary_table_peers(self, peer_ptrs):
+        arr, n = self._peer_array(peer_ptrs)
+        self._ck(lib().msm_unary_table_peers(self._h, arr, n))
+
+    def triplet_moves_range_peers(self, labeling_dev_ptr, alpha, t0, t1, peer_ptrs):
+        arr, n = self._peer_array(peer_ptrs)
+        self._ck(lib().msm_triplet_moves_range_peers(self._h, C.c_void_p(labeling_dev_ptr), int(alpha), int(t0), int(t1), arr, n))
 
     def pair_table(self):
         out = np.empty((self.P, self.L, self.L), np.float32)

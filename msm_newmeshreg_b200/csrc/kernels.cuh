@@ -501,7 +501,8 @@ __global__ void __launch_bounds__(128) k_triplet_queries(TripArgs a, int n, cons
 // fusion-move costs (include/Fusion/Fusion.h:187-194): combo bit2->A, bit1->B, bit0->C take label alpha.
 // alpha >= 0: out[t][8]; alpha < 0: all labels, out[alpha][t][8].
 template <typename OutT>
-__global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const int* __restrict__ labeling, int alpha, OutT* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const int* __restrict__ labeling, int alpha, OutT* __restrict__ out,
+                                                       PeerSet peers = PeerSet{}, int t_full = 0) {
     // one thread per (alpha, triplet): the triangle constants and the six candidate corners (current / alpha label of
     // each vertex) are formed once and shared by the 8 combinations
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -519,10 +520,22 @@ __global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const 
 #pragma unroll
         for (int j = 0; j < 3; j++) { pc[v][j] = c[j]; pa[v][j] = n[j]; }
     }
-    OutT* o = out + gid * 8;
+    float4 lo, hi;   // the 8 costs, also as two 16-byte stores for the fused exchange
+    OutT* o = peers.world > 0 ? nullptr : out + gid * 8;
 #pragma unroll
-    for (int combo = 0; combo < 8; combo++)
-        o[combo] = (OutT)trip_cost(a.p, g, (combo & 4) ? pa[0] : pc[0], (combo & 2) ? pa[1] : pc[1], (combo & 1) ? pa[2] : pc[2]);
+    for (int combo = 0; combo < 8; combo++) {
+        const OutT v = (OutT)trip_cost(a.p, g, (combo & 4) ? pa[0] : pc[0], (combo & 2) ? pa[1] : pc[1], (combo & 1) ? pa[2] : pc[2]);
+        if (o) o[combo] = v;
+        (&(combo < 4 ? lo : hi).x)[combo & 3] = (float)v;
+    }
+    if (peers.world > 0) {
+        // fused exchange (triplet sharding): straight into the full [L or 1][t_full][8] table of every rank
+        const size_t at = ((size_t)(alpha < 0 ? al : 0) * t_full + t) * 2;
+        for (int r = 0; r < peers.world; r++) {
+            float4* dst = reinterpret_cast<float4*>(peers.p[r]) + at;
+            dst[0] = lo; dst[1] = hi;
+        }
+    }
 }
 
 // full table: one CTA per triplet; displaced corners staged in shared memory; thread = (la,lb), loop lc;

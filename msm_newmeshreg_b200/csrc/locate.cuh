@@ -29,6 +29,14 @@ struct HintDev {
     const float4* hT;       // [20*4^h][3 edges][3 rows] : (T row, w of row 0 = neighbour face id as int bits)
 };
 
+// Destination tables of a fused exchange: device pointers, valid on THIS GPU, to the same buffer on every rank of a
+// control-point / triplet sharded run (CUDA IPC or symmetric-memory mappings over NVLink).  world == 0: not used.
+constexpr int kMaxPeers = 16;
+struct PeerSet {
+    float* p[kMaxPeers];
+    int world;
+};
+
 // 20 base faces: dual basis rows (alpha = A.p, beta = B.p, gamma = C.p) and centre directions.
 struct IcoBase {
     float dual[20][9];

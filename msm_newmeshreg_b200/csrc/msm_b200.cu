@@ -773,7 +773,29 @@ int msm_get_patches(msm_ctx* ctx, int* offsets, int* idx) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+static int make_peer_set(msm_ctx* ctx, void* const* peer_tables, int world, PeerSet& ps) {
+    if (world < 1 || world > kMaxPeers) FAIL("fused exchange: world size must be 1..16");
+    ps.world = world;
+    for (int r = 0; r < kMaxPeers; r++) ps.p[r] = r < world ? static_cast<float*>(peer_tables[r]) : nullptr;
+    for (int r = 0; r < world; r++)
+        if (!ps.p[r]) FAIL("fused exchange: null peer table");
+    return 0;
+}
+
+static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers);
+
 int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
+    PeerSet none{};
+    return unary_launch(ctx, d_out, none);
+}
+
+int msm_unary_table_peers(msm_ctx* ctx, void* const* peer_tables, int world) {
+    PeerSet ps{};
+    if (make_peer_set(ctx, peer_tables, world, ps)) return 1;
+    return unary_launch(ctx, nullptr, ps);
+}
+
+static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_target) FAIL("CostFunction::You must supply source and target meshes.");
     if (!ctx->have_patches) FAIL("get_source_data (msm_build_patches) must run before computeUnaryCosts");
@@ -815,6 +837,7 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
     a.ico = ico_dev(ctx);
     a.simmeasure = ctx->par.simmeasure;
     a.out = d_out;
+    a.peers = peers; a.n_full = ctx->N;
     const size_t tot = std::max<long long>(ctx->total, 1);
     CK(ctx->d_pcx.ensure(tot * 4)); CK(ctx->d_pcy.ensure(tot * 4)); CK(ctx->d_pcz.ensure(tot * 4));
     CK(ctx->d_hint_face.ensure((size_t)Ns * 4));
@@ -942,6 +965,23 @@ int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, 
     a.t_off = t0;
     Timer tm(ctx, "triplet_moves");
     k_triplet_moves<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, t1 - t0, d_labeling, alpha, d_out);
+    KLAUNCH_CHECK();
+    return 0;
+}
+
+int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, void* const* peer_tables, int world) {
+    CK(cudaSetDevice(ctx->device));
+    if (check_triplets(ctx)) return 1;
+    if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
+    if (t0 < 0 || t1 > ctx->Tn || t0 > t1) FAIL("msm_triplet_moves: bad triplet range");
+    PeerSet ps{};
+    if (make_peer_set(ctx, peer_tables, world, ps)) return 1;
+    if (t0 == t1) return 0;
+    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * (t1 - t0);
+    TripArgs a = trip_args(ctx);
+    a.t_off = t0;
+    Timer tm(ctx, "triplet_moves");
+    k_triplet_moves<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, t1 - t0, d_labeling, alpha, nullptr, ps, ctx->Tn);
     KLAUNCH_CHECK();
     return 0;
 }

@@ -147,6 +147,8 @@ struct UnaryArgs {
     HintDev hint;
     int simmeasure;
     float* out;                         // [L][Ns]
+    PeerSet peers;                      // optional (world > 0): label-major [L][n_full] tables, one per rank (peer mappings)
+    int n_full;
 };
 
 __device__ __forceinline__ double group8_sum(double v) {
@@ -420,7 +422,16 @@ __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
             cost = (double)AW * s;
         }
         if (!pos) cost = -cost;
-        if (act && sub == 0) a.out[(size_t)(l0 + l) * a.Ns + row] = (float)cost;
+        if (act && sub == 0) {
+            if (a.peers.world > 0) {
+                // fused exchange (control-point sharding): the finished entry goes straight into the label-major [L][N]
+                // table of EVERY rank through its peer mapping (NVLink stores) — no gather, no re-layout afterwards
+                const size_t at = (size_t)(l0 + l) * a.n_full + k;
+                for (int r = 0; r < a.peers.world; r++) a.peers.p[r][at] = (float)cost;
+            } else {
+                a.out[(size_t)(l0 + l) * a.Ns + row] = (float)cost;
+            }
+        }
     }
 }
 

@@ -409,3 +409,30 @@ def test_spatial_packing_order_only_reorders_sums(built, monkeypatch, C):
     assert pb.rel_err(tabs[1], tabs[0], 1e-2).max() < 2e-6
     cf = pb.oracle_costfunction(P); cf.get_source_data()
     assert pb.rel_err(tabs[1], cf.unary_costs(), 1e-2).max() < 1e-5
+
+
+def test_fused_exchange_kernels_fill_every_peer_table(built):
+    """msm_unary_table_peers / msm_triplet_moves_range_peers (control-point / triplet sharding): two shard contexts on one
+    GPU each store into BOTH "rank" tables; afterwards every table must be the complete single-context table, bit for bit."""
+    import torch
+    from msm_newmeshreg_b200 import sharding as sh
+    P = pb.make_problem(5, 3, 1, seed=7, warp=0.3, deform_cp=0.1)
+    ctx = pb.gpu_context(P); ctx.build_patches()
+    U = ctx.unary_table().astype(np.float32)
+    lab = np.random.default_rng(1).integers(0, P.L, P.N).astype(np.int32)
+    M = ctx.triplet_moves(lab, -1).astype(np.float32)
+    ctx.close()
+    world = 2
+    tabs_u = [torch.full((P.L, P.N), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
+    tabs_m = [torch.full((P.L, P.T, 8), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
+    lab_dev = torch.from_numpy(lab).cuda()
+    for r in range(world):
+        c = pb.gpu_context(P)
+        c.set_shard(*sh.shard_range(P.N, r, world)); c.build_patches()
+        c.unary_table_peers([t.data_ptr() for t in tabs_u])
+        t0, t1 = sh.shard_range(P.T, r, world)
+        c.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, [t.data_ptr() for t in tabs_m])
+        c.synchronize(); c.close()
+    for r in range(world):
+        assert np.array_equal(tabs_u[r].cpu().numpy(), U)
+        assert np.array_equal(tabs_m[r].cpu().numpy(), M)
