@@ -546,11 +546,13 @@ def main():
         peak, peak_src = measured_peak()
         unary_ms = um / max(un, 1)
         achieved = (np.mean(alg_bytes_unary) / (unary_ms * 1e-3)) / 1e9 if un else None
-        traffic = None
+        traffic = l2_traffic = l1_traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_unary_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("k_unary_dram_bytes_per_launch")
+                l2_traffic, l1_traffic = tj.get("k_unary_l2_bytes_per_launch"), tj.get("k_unary_l1_global_load_bytes_per_launch")
             except Exception:
                 traffic = None
         line = {
@@ -561,7 +563,8 @@ def main():
                        "evals_per_subject": evals_per_subject, "l2": "working set of B subjects per GPU exceeds the 126 MB L2 (no flush needed)",
                        "parallelism": f"subjects x{world} (no data-path collective)"},
             "roofline": {"bound": "hbm", "kernel": "k_unary", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_l2": l2_traffic,
+                         "traffic_l1_global_loads": l1_traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": float(np.mean(alg_bytes_unary)), "avg_launch_ms": unary_ms, "launches_timed": un,
                          "triplet_moves_avg_ms": tm_ / max(tn_, 1)},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e,
