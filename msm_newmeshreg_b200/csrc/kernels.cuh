@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256) k_face_pack(int F, int C, int Cp, int V, 
 struct TripGeom {            // per-triplet constants
     double n[3];             // (v1-v0)x(v2-v0) of the CURRENT control triangle (fold test)
     double G11, G12, G22;    // Gram of the ORIGINAL triangle
-    double det0;
+    double det0, idet0;
     double oang[3], oarea;   // rmode 2
 };
 
@@ -410,6 +410,7 @@ __device__ __forceinline__ void trip_geom(const DevParams& p, const double* v0, 
     for (int j = 0; j < 3; j++) { E1[j] = o1[j] - o0[j]; E2[j] = o2[j] - o0[j]; }
     g.G11 = dot3(E1, E1); g.G12 = dot3(E1, E2); g.G22 = dot3(E2, E2);
     g.det0 = g.G11 * g.G22 - g.G12 * g.G12;
+    g.idet0 = 1.0 / g.det0;
     if (p.rmode == 2 && !p.group) {
         tri_angles(o0, o1, o2, g.oang);
         double c[3]; cross3(E1, E2, c);
@@ -419,8 +420,8 @@ __device__ __forceinline__ void trip_geom(const DevParams& p, const double* v0, 
 
 // strain energy from Gram entries; k_exp == 2 avoids sqrt/pow: R^2+R^-2-2 = I1*^2-4, J^2 = I3
 __device__ __forceinline__ double strain_energy(double g11, double g12, double g22, const TripGeom& g, double mu, double kappa, double k_exp) {
-    const double trC = (g11 * g.G22 - 2.0 * g12 * g.G12 + g22 * g.G11) / g.det0;
-    const double I3 = (g11 * g22 - g12 * g12) / g.det0;
+    const double trC = (g11 * g.G22 - 2.0 * g12 * g.G12 + g22 * g.G11) * g.idet0;   // one reciprocal per triplet, not
+    const double I3 = (g11 * g22 - g12 * g12) * g.idet0;                            // two divisions per evaluation
     if (k_exp == 2.0) {
         const double r = 1.0 / I3;
         const double i1s2 = trC * trC * r;  // (I1*)^2
