@@ -116,7 +116,7 @@ struct msm_ctx {
     DevBuf d_vkey;            // [Vs] spatial sort key of every source vertex (k_vertex_key)
     bool vkey_valid = false;
     DevBuf d_cell_counts, d_cell_start, d_cell_fill, d_cell_of, d_sorted;  // voxel grid of the source vertices
-    DevBuf d_pcx, d_pcy, d_pcz, d_hint_face, d_lab12, d_tref, d_x0;  // k_cp_hint / k_unary_setup outputs
+    DevBuf d_pcx, d_pcy, d_pcz, d_hint_face, d_lab12, d_tref;  // k_unary_setup outputs
     int pack_cp = 0;
 
     DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
@@ -857,10 +857,7 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
         s.tref = ctx->d_tref.as<float>();
         s.face_feat = CQ == 0 ? ctx->d_face_feat.as<float>() : nullptr;
         s.pcx = ctx->d_pcx.as<float>(); s.pcy = ctx->d_pcy.as<float>(); s.pcz = ctx->d_pcz.as<float>();
-        CK(ctx->d_x0.ensure((size_t)Ns * 3 * sizeof(double)));
-        k_cp_hint<<<(Ns + 127) / 128, 128, 0, ctx->stream>>>(s, Ns, ctx->d_x0.as<double>());
-        KLAUNCH_CHECK();
-        k_unary_setup<<<Ns, 128, 0, ctx->stream>>>(s, ctx->d_x0.as<double>());
+        k_unary_setup<<<(Ns + 3) / 4, 128, 0, ctx->stream>>>(s, Ns);
         KLAUNCH_CHECK();
     }
 #define LAUNCH_UNARY(Q)                                                                                             \

@@ -1,6 +1,6 @@
 // unary.cuh — the unary data term (src/DiscreteCostFunction.cpp:306-313,412-448,483-526; similarities.cc:122-173).
 //
-// k_unary_setup (fp64, one CTA per control point k): the level-h "hint" face under CP_k, CP_k's corner coordinates in
+// k_unary_setup (fp64, one warp per control point k): the level-h "hint" face under CP_k, CP_k's corner coordinates in
 //   it, and from those
 //     per sample i :  c_i = x(CP_k) + A r_i           (r_i = SRC_i - CP_k, the packed offsets)
 //     per label  l :  M_l = A (R_kl - I),  g_l = A (R_kl - I) CP_k
@@ -67,54 +67,51 @@ struct UnarySetupArgs {
     float* pcx; float* pcy; float* pcz; // [total] corner coordinates of the unrotated samples
 };
 
-// one THREAD per control point: hint face, its dual basis applied to CP_k, and the reference target value — the only
-// serial fp64 descents of the set-up, taken out of k_unary_setup so that no CTA waits on a single thread
-__global__ void __launch_bounds__(128) k_cp_hint(UnarySetupArgs a, int Ns, double* __restrict__ x0_out /*[Ns][3]*/) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= Ns) return;
+// One WARP per control point (4 per CTA, no block barrier): lane 0 walks the fp64 hierarchy — hint face, then on to the
+// leaf for the reference target value — the other lanes then form, from the hint face's dual basis A,
+//     per sample i :  c_i = A CP_k + A r_i     and     per label l :  M_l = A K_kl,  g_l = A K_kl CP_k.
+__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= Ns) return;   // whole warps leave together
     const int k = a.k_begin + row;
     const double ox = a.cp[3 * k], oy = a.cp[3 * k + 1], oz = a.cp[3 * k + 2];
-    int base, n; double al, be, ga;
-    descend_d(a.ico, a.hint.h, ox, oy, oz, base, n, al, be, ga);
-    const int f = base * a.hint.nf_per_base + (n - a.hint.node_off);
-    a.hint_face[row] = f;
-    const double* Ag = a.hint.hdual + (size_t)f * 9;
-    x0_out[3 * row + 0] = Ag[0] * ox + Ag[1] * oy + Ag[2] * oz;
-    x0_out[3 * row + 1] = Ag[3] * ox + Ag[4] * oy + Ag[5] * oz;
-    x0_out[3 * row + 2] = Ag[6] * ox + Ag[7] * oy + Ag[8] * oz;
-    float tr = 0.f;
-    if (a.face_feat) {  // continue the same descent down to the leaf
-        for (int l = a.hint.h; l < a.ico.depth; l++) {
-            const double4 nn = a.ico.ntab_d[n];
-            const double s = al + be + ga;
-            const double sa = (al + al) - s, sb = (be + be) - s, sc = (ga + ga) - s;
-            int child; double x, y, z;
-            if (sa > 0.0) { child = 0; x = sa; y = be * nn.x; z = ga * nn.z; }
-            else if (sb > 0.0) { child = 1; x = al * nn.x; y = sb; z = ga * nn.y; }
-            else if (sc > 0.0) { child = 2; x = al * nn.z; y = be * nn.y; z = sc; }
-            else { child = 3; x = -sa * nn.y; y = -sb * nn.z; z = -sc * nn.x; }
-            al = x; be = y; ga = z;
-            n = 4 * n + 1 + child;
+    int f = 0;
+    if (lane == 0) {
+        int base, n; double al, be, ga;
+        descend_d(a.ico, a.hint.h, ox, oy, oz, base, n, al, be, ga);
+        f = base * a.hint.nf_per_base + (n - a.hint.node_off);
+        a.hint_face[row] = f;
+        float tr = 0.f;
+        if (a.face_feat) {  // continue the same descent down to the leaf
+            for (int l = a.hint.h; l < a.ico.depth; l++) {
+                const double4 nn = a.ico.ntab_d[n];
+                const double s = al + be + ga;
+                const double sa = (al + al) - s, sb = (be + be) - s, sc = (ga + ga) - s;
+                int child; double x, y, z;
+                if (sa > 0.0) { child = 0; x = sa; y = be * nn.x; z = ga * nn.z; }
+                else if (sb > 0.0) { child = 1; x = al * nn.x; y = sb; z = ga * nn.y; }
+                else if (sc > 0.0) { child = 2; x = al * nn.z; y = be * nn.y; z = sc; }
+                else { child = 3; x = -sa * nn.y; y = -sb * nn.z; z = -sc * nn.x; }
+                al = x; be = y; ga = z;
+                n = 4 * n + 1 + child;
+            }
+            tr = reinterpret_cast<const float4*>(a.face_feat)[base * a.ico.nleaf_per_base + (n - a.ico.leaf_off)].x;
         }
-        tr = reinterpret_cast<const float4*>(a.face_feat)[base * a.ico.nleaf_per_base + (n - a.ico.leaf_off)].x;
+        a.tref[row] = tr;
     }
-    a.tref[row] = tr;
-}
-
-__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, const double* __restrict__ x0_in) {
-    const int row = blockIdx.x, k = a.k_begin + row, tid = threadIdx.x;
-    __shared__ double A[9], x0[3];
-    const double ox = a.cp[3 * k], oy = a.cp[3 * k + 1], oz = a.cp[3 * k + 2];
-    if (tid < 9) A[tid] = a.hint.hdual[(size_t)a.hint_face[row] * 9 + tid];
-    else if (tid < 12) x0[tid - 9] = x0_in[3 * row + tid - 9];
-    __syncthreads();
-    for (int s = a.off[row] + tid; s < a.off[row + 1]; s += 128) {
+    f = __shfl_sync(0xffffffffu, f, 0);
+    double A[9];   // same address in every lane: one broadcast transaction each
+#pragma unroll
+    for (int j = 0; j < 9; j++) A[j] = a.hint.hdual[(size_t)f * 9 + j];
+    const double x0 = A[0] * ox + A[1] * oy + A[2] * oz, x1 = A[3] * ox + A[4] * oy + A[5] * oz, x2 = A[6] * ox + A[7] * oy + A[8] * oz;
+    for (int s = a.off[row] + lane; s < a.off[row + 1]; s += 32) {
         const double x = a.px[s], y = a.py[s], z = a.pz[s];
-        a.pcx[s] = (float)(x0[0] + (A[0] * x + A[1] * y + A[2] * z));
-        a.pcy[s] = (float)(x0[1] + (A[3] * x + A[4] * y + A[5] * z));
-        a.pcz[s] = (float)(x0[2] + (A[6] * x + A[7] * y + A[8] * z));
+        a.pcx[s] = (float)(x0 + (A[0] * x + A[1] * y + A[2] * z));
+        a.pcy[s] = (float)(x1 + (A[3] * x + A[4] * y + A[5] * z));
+        a.pcz[s] = (float)(x2 + (A[6] * x + A[7] * y + A[8] * z));
     }
-    for (int l = tid; l < a.L; l += 128) {
+    for (int l = lane; l < a.L; l += 32) {
         const double* K = a.Kd + ((size_t)k * a.L + l) * 9;
         // the control point itself moves by (R-I) CP_k (no cancellation: K holds R-I at full precision)
         const double dx = K[0] * ox + K[1] * oy + K[2] * oz, dy = K[3] * ox + K[4] * oy + K[5] * oz, dz = K[6] * ox + K[7] * oy + K[8] * oz;
