@@ -365,6 +365,104 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
         dist.barrier(); dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------- groupwise mode
+def bench_group(args, rank, world, local, metric, unit):
+    """BASELINE.json configs[4]: groupwise registration (DiscreteGroupModel) of S subjects with group triplet costs
+    (src/DiscreteGroupCostFunction.cpp:9-30), subjects sharded over the GPUs.  The S control meshes are replicated (S*N
+    points, small); each GPU evaluates the fusion-move triplet costs of every label for ITS subjects' triangles and stores
+    them straight into every rank's [L][S*T][8] table over peer mappings (fused exchange), one barrier per step — the joint
+    host optimiser needs the whole table.  A sample of the table is checked against the oracle port and, when built, the
+    reference's own DiscreteGroupCostFunction."""
+    import torch
+    import torch.distributed as dist
+    from msm_newmeshreg_b200 import Context, sharding
+    from oracle import pyorc, pyrefcost
+    S, lvl = args.group_subjects, args.group_cp_level
+    cxyz0, ctris = pyorc.icosphere(lvl)
+    maxsep, mvdmax, mvd = pyorc.spacings(cxyz0, ctris)
+    samples, bary, centre = pyorc.label_grid(lvl + 2, 0.5 * mvdmax)
+    trip1 = pyorc.triplets(cxyz0, ctris)
+    N, T, L = len(cxyz0), len(trip1), len(bary)
+    cps = np.stack([smooth_warp(cxyz0, 500 + s, 0.25 * mvd) for s in range(S)])
+    trip = np.concatenate([trip1 + s * N for s in range(S)]).astype(np.int32)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
+    lam, mu, kappa = f32(0.2), f32(0.4), f32(1.6)
+    ctx = Context(local)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_params(lam=lam, rexp=2.0, mu=mu, kappa=kappa, rmode=3, group=True)
+    ctx.set_cpgrid(cps.reshape(-1, 3), np.zeros((0, 3), np.int32), np.ones(S * N), np.tile(cxyz0, (S, 1)))
+    ctx.set_group(S, N, T)
+    ctx.set_labels(bary, centre)
+    ctx.set_triplets(trip)
+    lab = np.random.default_rng(7).integers(0, L, S * N).astype(np.int32)
+    lab_dev = torch.from_numpy(lab).cuda()
+    s0, s1 = sharding.shard_range(S, rank, world)        # whole subjects per rank
+    t0, t1 = s0 * T, s1 * T
+    hdl = None
+    if world > 1:
+        import torch.distributed._symmetric_memory as symm_mem
+        full = symm_mem.empty(L * S * T * 8, dtype=torch.float32, device=f"cuda:{local}")
+        hdl = symm_mem.rendezvous(full, dist.group.WORLD)
+        peers = [int(p) for p in hdl.buffer_ptrs]
+    else:
+        full = torch.empty(L * S * T * 8, dtype=torch.float32, device="cuda")
+        peers = [full.data_ptr()]
+
+    def step():
+        ctx.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, peers)
+        if hdl is not None:
+            hdl.barrier(channel=0)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    # parity of a sample of the assembled table (every rank holds all of it)
+    M = full.view(L, S * T, 8).cpu().numpy()
+    rng = np.random.default_rng(3)
+    qa, qt, qc = rng.integers(0, L, 4000), rng.integers(0, S * T, 4000), rng.integers(0, 8, 4000)
+    q = np.stack([qt, np.where(qc & 4, qa, lab[trip[qt, 0]]), np.where(qc & 2, qa, lab[trip[qt, 1]]), np.where(qc & 1, qa, lab[trip[qt, 2]])], 1).astype(np.int32)
+    rot = np.concatenate([pyorc.rotations(centre, cps[s]) for s in range(S)])
+    got = M[qa, qt, qc].astype(np.float64)
+    checks = {}
+    for name, G in (("oracle", pyorc.GroupCost), ("reference", pyrefcost.GroupCost if pyrefcost.available() else None)):
+        if G is None:
+            continue
+        g = G(); g.set(lam, 2.0, mu, kappa, cps, ctris, cxyz0, bary, rot, trip)
+        want = g.triplet_costs(q)
+        checks[name] = float((np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * lam)).max())
+        assert checks[name] < 1e-5, (name, checks[name])
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    evals = L * S * T * 8
+    if rank == 0:
+        print(json.dumps({
+            "metric": metric, "value": evals / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"groupwise (BASELINE.json configs[4]): {S} subjects, ico{lvl} control grids ({N} points, {T} triangles each), "
+                                   f"L={L}; step = group fusion-move triplet costs of every label, subjects sharded over {world} GPU(s), table "
+                                   f"assembled on every rank by peer stores (fused exchange)",
+                       "S": S, "N": N, "T": T, "L": L, "table_bytes": 4 * evals, "max_rel_err_of_sample": checks},
+            "gpu_launches": int(ctx.launch_count() - launches0)}))
+    ctx.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -377,9 +475,12 @@ def main():
     ap.add_argument("--cp-level", type=int, default=5)
     ap.add_argument("--channels", type=int, default=1)
     ap.add_argument("--cpu-rows", type=int, default=1024, help="control points in the bounded CPU sample")
-    ap.add_argument("--mode", default="subjects", choices=["subjects", "cp"],
+    ap.add_argument("--mode", default="subjects", choices=["subjects", "cp", "group"],
                     help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
-                         "and triplets sharded over the GPUs, table slices all-gathered with NCCL (strong scaling)")
+                         "and triplets sharded over the GPUs (strong scaling); group: groupwise registration "
+                         "(DiscreteGroupCostFunction triplet costs of --group-subjects subjects, subjects sharded over the GPUs)")
+    ap.add_argument("--group-subjects", type=int, default=16)
+    ap.add_argument("--group-cp-level", type=int, default=4)
     ap.add_argument("--cp-exchange", default="p2p", choices=["p2p", "nccl"],
                     help="--mode cp: p2p = kernels store into every rank's table through symmetric-memory peer mappings "
                          "(fused exchange); nccl = all_gather_into_tensor + re-layout")
@@ -432,6 +533,8 @@ def main():
 
     if args.mode == "cp":
         return bench_cp_sharded(args, rank, world, local, C, metric, unit)
+    if args.mode == "group":
+        return bench_group(args, rank, world, local, metric, unit)
     B = args.subjects_per_gpu
     txyz, ttris = host.icosphere(args.data_level)
     cxyz0, ctris = host.icosphere(args.cp_level)
