@@ -296,7 +296,7 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
     # may overwrite them; the bench only reads after the last step.)
     exchange, why = args.cp_exchange, ""
     full_u = full_m = hdl = None
-    if exchange == "p2p":
+    if exchange in ("p2p", "mc"):
         try:
             if world > 1:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -305,28 +305,33 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
                 hdl = symm_mem.rendezvous(full_u, dist.group.WORLD)
                 hdl_m = symm_mem.rendezvous(full_m, dist.group.WORLD)
                 peer_u, peer_m = [int(p) for p in hdl.buffer_ptrs], [int(p) for p in hdl_m.buffer_ptrs]
+                mc_u, mc_m = int(getattr(hdl, "multicast_ptr", 0) or 0), int(getattr(hdl_m, "multicast_ptr", 0) or 0)
+                if exchange == "mc" and not (mc_u and mc_m):
+                    exchange, why = "p2p", " (no NVSwitch multicast address on this box: plain peer stores)"
             else:
                 full_u = torch.empty(L * N, dtype=torch.float32, device="cuda")
                 full_m = torch.empty(L * T * 8, dtype=torch.float32, device="cuda")
                 peer_u, peer_m = [full_u.data_ptr()], [full_m.data_ptr()]
+                mc_u = mc_m = 0
+                exchange = "p2p"
         except Exception as e:   # no symmetric memory on this box: fall back to the NCCL gather
             exchange, why = "nccl", f" (p2p unavailable: {type(e).__name__}: {e})"
 
     def step_p2p():
-        ctx.unary_table_peers(peer_u)
-        ctx.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, peer_m)
+        ctx.unary_table_peers(peer_u, mc_u if exchange == "mc" else 0)
+        ctx.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, peer_m, mc_m if exchange == "mc" else 0)
         if hdl is not None:
             hdl.barrier(channel=0)
         return full_u.view(L, N), full_m.view(L, T * 8)
 
-    if exchange == "p2p":   # the two exchanges must produce the same tables
+    if exchange in ("p2p", "mc"):   # the exchanges must produce the same tables
         Un, Mn = step_nccl()
         Up, Mp = step_p2p()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier(); torch.cuda.synchronize()
         assert torch.equal(Un, Up) and torch.equal(Mn.reshape(L, -1), Mp), "fused exchange differs from the NCCL gather"
-    step = step_p2p if exchange == "p2p" else step_nccl
+    step = step_p2p if exchange in ("p2p", "mc") else step_nccl
 
     def sync_all():
         torch.cuda.synchronize()
@@ -356,8 +361,9 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
             "dtype": "f32 (unary) / f64 (triplet)", "data": "synthetic",
             "config": {"workload": f"C3 CP-sharded: ONE ico{args.data_level}/ico{args.cp_level} registration, control points and triplets "
                                    f"split over {world} GPU(s), unary [L][N] and fusion-move [L][T][8] tables "
-                                   + ("written by the kernels straight into every rank's table over NVLink peer mappings (fused exchange, "
-                                      "one device-side barrier per step)" if exchange == "p2p" else "gathered with NCCL all_gather" + why),
+                                   + ("written by the kernels straight into every rank's table (fused exchange: "
+                                      + ("ONE NVSwitch multicast store per entry" if exchange == "mc" else "one NVLink peer store per rank and entry")
+                                      + ", one device-side barrier per step)" + why if exchange in ("p2p", "mc") else "gathered with NCCL all_gather" + why),
                        "exchange": exchange, "N": N, "L": L, "T": T, "gathered_bytes_per_step": 4 * (L * N + L * T * 8),
                        "l2": "single subject: inputs are L2 resident between steps (mode used to show the sharded path, not the headline)"},
             "gpu_launches": int(ctx.launch_count() - launches0), "checksum": checksum}))
@@ -404,12 +410,13 @@ def bench_group(args, rank, world, local, metric, unit):
         full = symm_mem.empty(L * S * T * 8, dtype=torch.float32, device=f"cuda:{local}")
         hdl = symm_mem.rendezvous(full, dist.group.WORLD)
         peers = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if args.cp_exchange == "mc" else 0
     else:
         full = torch.empty(L * S * T * 8, dtype=torch.float32, device="cuda")
-        peers = [full.data_ptr()]
+        peers, mc = [full.data_ptr()], 0
 
     def step():
-        ctx.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, peers)
+        ctx.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, peers, mc)
         if hdl is not None:
             hdl.barrier(channel=0)
 
@@ -455,7 +462,7 @@ def bench_group(args, rank, world, local, metric, unit):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"groupwise (BASELINE.json configs[4]): {S} subjects, ico{lvl} control grids ({N} points, {T} triangles each), "
                                    f"L={L}; step = group fusion-move triplet costs of every label, subjects sharded over {world} GPU(s), table "
-                                   f"assembled on every rank by peer stores (fused exchange)",
+                                   f"assembled on every rank by " + ("NVSwitch multicast stores" if mc else "peer stores") + " (fused exchange)",
                        "S": S, "N": N, "T": T, "L": L, "table_bytes": 4 * evals, "max_rel_err_of_sample": checks},
             "gpu_launches": int(ctx.launch_count() - launches0)}))
     ctx.close()
@@ -481,9 +488,10 @@ def main():
                          "(DiscreteGroupCostFunction triplet costs of --group-subjects subjects, subjects sharded over the GPUs)")
     ap.add_argument("--group-subjects", type=int, default=16)
     ap.add_argument("--group-cp-level", type=int, default=4)
-    ap.add_argument("--cp-exchange", default="p2p", choices=["p2p", "nccl"],
-                    help="--mode cp: p2p = kernels store into every rank's table through symmetric-memory peer mappings "
-                         "(fused exchange); nccl = all_gather_into_tensor + re-layout")
+    ap.add_argument("--cp-exchange", default="mc", choices=["mc", "p2p", "nccl"],
+                    help="--mode cp / group: mc = kernels store each entry ONCE to the NVSwitch multicast address of the table "
+                         "(falls back to p2p); p2p = one peer store per rank through symmetric-memory mappings; "
+                         "nccl = all_gather_into_tensor + re-layout (cp mode only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

@@ -123,9 +123,13 @@ int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, 
  * mappings over NVLink; peer_tables[own rank] is the local buffer.
  *   msm_unary_table_peers        : float[L][N], rows [k_begin,k_end) of this context's shard (msm_set_shard)
  *   msm_triplet_moves_range_peers: float[L or 1][T][8], triplets [t0,t1)
+ * multicast_table (may be NULL): the NVSwitch multicast address of the same buffer (cuMulticast* / symmetric memory's
+ * multicast_ptr); when given, each entry is written with ONE multimem.st that the switch replicates to every rank (NVLS)
+ * instead of `world` peer stores.
  * Launched on the context stream; the caller makes the ranks wait for each other afterwards (a barrier on the stream). */
-int msm_unary_table_peers(msm_ctx* ctx, void* const* peer_tables, int world);
-int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, void* const* peer_tables, int world);
+int msm_unary_table_peers(msm_ctx* ctx, void* const* peer_tables, int world, void* multicast_table);
+int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, void* const* peer_tables, int world,
+                                  void* multicast_table);
 
 /* computePairwiseCosts (src/DiscreteCostFunction.cpp:256-304): out float[P][L][L] in the reference layout. */
 int msm_pair_table(msm_ctx* ctx, float* out);

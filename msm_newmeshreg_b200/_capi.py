@@ -233,13 +233,14 @@ class Context:
         arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
         return arr, len(peer_ptrs)
 
-    def unary_table_peers(self, peer_ptrs):
+    def unary_table_peers(self, peer_ptrs, multicast_ptr=0):
         arr, n = self._peer_array(peer_ptrs)
-        self._ck(lib().msm_unary_table_peers(self._h, arr, n))
+        self._ck(lib().msm_unary_table_peers(self._h, arr, n, C.c_void_p(int(multicast_ptr) or None)))
 
-    def triplet_moves_range_peers(self, labeling_dev_ptr, alpha, t0, t1, peer_ptrs):
+    def triplet_moves_range_peers(self, labeling_dev_ptr, alpha, t0, t1, peer_ptrs, multicast_ptr=0):
         arr, n = self._peer_array(peer_ptrs)
-        self._ck(lib().msm_triplet_moves_range_peers(self._h, C.c_void_p(labeling_dev_ptr), int(alpha), int(t0), int(t1), arr, n))
+        self._ck(lib().msm_triplet_moves_range_peers(self._h, C.c_void_p(labeling_dev_ptr), int(alpha), int(t0), int(t1), arr, n,
+                                                     C.c_void_p(int(multicast_ptr) or None)))
 
     def pair_table(self):
         out = np.empty((self.P, self.L, self.L), np.float32)

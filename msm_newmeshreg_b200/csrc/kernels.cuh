@@ -532,9 +532,14 @@ __global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const 
     if (peers.world > 0) {
         // fused exchange (triplet sharding): straight into the full [L or 1][t_full][8] table of every rank
         const size_t at = ((size_t)(alpha < 0 ? al : 0) * t_full + t) * 2;
-        for (int r = 0; r < peers.world; r++) {
-            float4* dst = reinterpret_cast<float4*>(peers.p[r]) + at;
-            dst[0] = lo; dst[1] = hi;
+        if (peers.mc) {
+            float4* dst = reinterpret_cast<float4*>(peers.mc) + at;
+            multicast_store(dst, lo); multicast_store(dst + 1, hi);
+        } else {
+            for (int r = 0; r < peers.world; r++) {
+                float4* dst = reinterpret_cast<float4*>(peers.p[r]) + at;
+                dst[0] = lo; dst[1] = hi;
+            }
         }
     }
 }

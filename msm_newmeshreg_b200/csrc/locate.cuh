@@ -34,8 +34,16 @@ struct HintDev {
 constexpr int kMaxPeers = 16;
 struct PeerSet {
     float* p[kMaxPeers];
+    float* mc;      // optional NVSwitch multicast address of the same buffer: ONE store reaches every rank
     int world;
 };
+// multimem.st: the store is replicated to all GPUs of the multicast object by the switch (NVLS)
+__device__ __forceinline__ void multicast_store(float* addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multicast_store(float4* addr, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // 20 base faces: dual basis rows (alpha = A.p, beta = B.p, gamma = C.p) and centre directions.
 struct IcoBase {

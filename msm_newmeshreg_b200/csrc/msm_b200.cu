@@ -773,9 +773,10 @@ int msm_get_patches(msm_ctx* ctx, int* offsets, int* idx) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-static int make_peer_set(msm_ctx* ctx, void* const* peer_tables, int world, PeerSet& ps) {
+static int make_peer_set(msm_ctx* ctx, void* const* peer_tables, int world, void* multicast_table, PeerSet& ps) {
     if (world < 1 || world > kMaxPeers) FAIL("fused exchange: world size must be 1..16");
     ps.world = world;
+    ps.mc = static_cast<float*>(multicast_table);
     for (int r = 0; r < kMaxPeers; r++) ps.p[r] = r < world ? static_cast<float*>(peer_tables[r]) : nullptr;
     for (int r = 0; r < world; r++)
         if (!ps.p[r]) FAIL("fused exchange: null peer table");
@@ -789,9 +790,9 @@ int msm_unary_table_dev(msm_ctx* ctx, float* d_out) {
     return unary_launch(ctx, d_out, none);
 }
 
-int msm_unary_table_peers(msm_ctx* ctx, void* const* peer_tables, int world) {
+int msm_unary_table_peers(msm_ctx* ctx, void* const* peer_tables, int world, void* multicast_table) {
     PeerSet ps{};
-    if (make_peer_set(ctx, peer_tables, world, ps)) return 1;
+    if (make_peer_set(ctx, peer_tables, world, multicast_table, ps)) return 1;
     return unary_launch(ctx, nullptr, ps);
 }
 
@@ -966,13 +967,14 @@ int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, 
     return 0;
 }
 
-int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, void* const* peer_tables, int world) {
+int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, void* const* peer_tables, int world,
+                                  void* multicast_table) {
     CK(cudaSetDevice(ctx->device));
     if (check_triplets(ctx)) return 1;
     if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
     if (t0 < 0 || t1 > ctx->Tn || t0 > t1) FAIL("msm_triplet_moves: bad triplet range");
     PeerSet ps{};
-    if (make_peer_set(ctx, peer_tables, world, ps)) return 1;
+    if (make_peer_set(ctx, peer_tables, world, multicast_table, ps)) return 1;
     if (t0 == t1) return 0;
     const long long n = (long long)(alpha < 0 ? ctx->L : 1) * (t1 - t0);
     TripArgs a = trip_args(ctx);

@@ -424,7 +424,9 @@ __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
                 // fused exchange (control-point sharding): the finished entry goes straight into the label-major [L][N]
                 // table of EVERY rank through its peer mapping (NVLink stores) — no gather, no re-layout afterwards
                 const size_t at = (size_t)(l0 + l) * a.n_full + k;
-                for (int r = 0; r < a.peers.world; r++) a.peers.p[r][at] = (float)cost;
+                if (a.peers.mc) multicast_store(a.peers.mc + at, (float)cost);
+                else
+                    for (int r = 0; r < a.peers.world; r++) a.peers.p[r][at] = (float)cost;
             } else {
                 a.out[(size_t)(l0 + l) * a.Ns + row] = (float)cost;
             }
