@@ -633,9 +633,9 @@ def main():
             models[s].reset_meshspace(sx.numpy())
             models[s].reset_cpgrid(cx.numpy())
             models[s].setup()                       # patch construction + unary table -> host double[L][N]
-            models[s].triplet_moves(lab_host, -1, out=moves_host.numpy())   # -> pinned host double[L][T][8]
+            models[s].triplet_moves(lab_host, -1, out=moves_host.numpy())   # -> pinned host float[L][T][8] (fp32 table)
 
-    moves_host = torch.empty((L, T, 8), dtype=torch.float64).pin_memory()
+    moves_host = torch.empty((L, T, 8), dtype=torch.float32).pin_memory()
     for _ in range(1):
         e2e_step()
     sync_all()
@@ -654,7 +654,7 @@ def main():
     e2e_value = evals_per_subject * B * world / float(t.item())
     Vs = len(txyz)
     h2d = B * (Vs * 24 + N * 24 + N * 4)
-    d2h = B * (L * N * 4 + L * T * 8 * 8)
+    d2h = B * (L * N * 4 + L * T * 8 * 4)
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -113,6 +113,7 @@ int msm_triplet_costs(msm_ctx* ctx, int n, const int* q, double* out);
 int msm_triplet_table(msm_ctx* ctx, int t0, int t1, float* out);
 int msm_triplet_table_dev(msm_ctx* ctx, int t0, int t1, float* d_out);
 int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out);
+int msm_triplet_moves_f32(msm_ctx* ctx, const int* labeling, int alpha, float* out); /* same table, fp32: half the read-back */
 int msm_triplet_moves_dev(msm_ctx* ctx, const int* d_labeling, int alpha, float* d_out);
 /* Multi-GPU: the same for the triplet shard [t0,t1): d_out float[L or 1][t1-t0][8]. */
 int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, float* d_out);

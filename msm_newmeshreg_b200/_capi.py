@@ -27,7 +27,7 @@ EXPORTS = [
     "msm_set_target", "msm_set_source", "msm_reset_source", "msm_set_cpgrid", "msm_reset_cpgrid", "msm_set_shard", "msm_set_labels",
     "msm_set_pairs", "msm_set_triplets", "msm_set_group", "msm_build_patches", "msm_patch_count", "msm_get_patches",
     "msm_unary_table", "msm_unary_table_dev", "msm_triplet_costs", "msm_triplet_table", "msm_triplet_table_dev", "msm_triplet_moves",
-    "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count",
+    "msm_triplet_moves_f32", "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count",
     "msm_set_timing", "msm_last_kernel_ms", "msm_timing_collect", "msm_set_group_patches", "msm_group_pair_costs",
     "msm_group_pair_moves", "msm_mesh_interpolate",
 ]

@@ -1010,6 +1010,28 @@ int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out)
     return 0;
 }
 
+// the same table in fp32 (the stated tolerance of the cost tables is 1e-5 relative): half the read-back
+int msm_triplet_moves_f32(msm_ctx* ctx, const int* labeling, int alpha, float* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (check_triplets(ctx)) return 1;
+    if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
+    for (int i = 0; i < ctx->N; i++)
+        if (labeling[i] < 0 || labeling[i] >= ctx->L) FAIL("msm_triplet_moves: labeling out of range");
+    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * ctx->Tn * 8;
+    CK(ctx->d_scratch.ensure((size_t)ctx->N * 4));
+    CK(ctx->d_scratch2.ensure((size_t)n * 4));
+    CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        Timer tm(ctx, "triplet_moves");
+        k_triplet_moves<float><<<(unsigned)((n / 8 + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha,
+                                                                                  ctx->d_scratch2.as<float>());
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 static int check_pairs(msm_ctx* ctx) {
     if (ctx->P <= 0) FAIL("set_pairs must be called first");

@@ -179,5 +179,8 @@ class Model:
         labeling, p = _i(labeling)
         if out is None:
             out = np.empty((self.L, self.T, 8) if alpha < 0 else (self.T, 8))
-        self._ck(self._L.msmhost_model_triplet_moves(self.h, p, int(alpha), out.ctypes.data_as(c_dp)))
+        if out.dtype == np.float32:   # fp32 table (GPU-backed library only): half the read-back
+            self._ck(self._L.msmhost_model_triplet_moves_f32(self.h, p, int(alpha), out.ctypes.data_as(C.POINTER(C.c_float))))
+        else:
+            self._ck(self._L.msmhost_model_triplet_moves(self.h, p, int(alpha), out.ctypes.data_as(c_dp)))
         return out

@@ -306,6 +306,10 @@ int msmhost_model_triplet_moves(void* h, const int* labeling, int alpha, double*
     auto* b = (ModelBox*)h;
     return guard([&] { b->model->getNonLinearCostFunction()->computeTripletMoves(labeling, alpha, out); });
 }
+int msmhost_model_triplet_moves_f32(void* h, const int* labeling, int alpha, float* out) {
+    auto* b = (ModelBox*)h;
+    return guard([&] { b->model->getNonLinearCostFunction()->computeTripletMoves(labeling, alpha, out); });
+}
 #else
 // the reference has no batched move evaluation: the same [L][T][8] / [T][8] layout from its per-element virtual
 // (include/Fusion/Fusion.h:187-194 bit order: bit2 -> A, bit1 -> B, bit0 -> C take the proposal label)

@@ -158,6 +158,10 @@ public:
         sync_device_state();
         check(msm_triplet_moves(ctx, labeling, alpha, out));
     }
+    void computeTripletMoves(const int* labeling, int alpha, float* out) {  // fp32 table: half the read-back
+        sync_device_state();
+        check(msm_triplet_moves_f32(ctx, labeling, alpha, out));
+    }
 
     void set_dataaffintyweighting(const NEWMAT::Matrix& HRWeight) { _HIGHREScfweight = HRWeight; source_dirty = true; }
 

@@ -198,3 +198,15 @@ def test_run_discrete_opt_gpu_equals_reference_end_to_end(built, dopt, rmode):
     d_sing = np.linalg.norm(P.txyz - P.cxyz0[sing[0]], axis=1) if len(sing) else np.full(len(P.txyz), 1e9)
     assert np.abs(sg - sr)[d_sing > 2.5 * P.mvdmax].max() < 1e-4
     g.close(); r.close()
+
+
+def test_triplet_moves_fp32_variant_is_the_rounded_fp64_table(built):
+    P = pb.make_problem(4, 2, 1, seed=81, warp=0.3, deform_cp=0.1)
+    m = _model(P, rmode=3); m.reset_cpgrid(P.cxyz); m.setup()
+    lab = np.random.default_rng(2).integers(0, m.L, m.N).astype(np.int32)
+    d = m.triplet_moves(lab, -1)
+    f = m.triplet_moves(lab, -1, out=np.empty((m.L, m.T, 8), np.float32))
+    assert f.dtype == np.float32 and np.array_equal(f, d.astype(np.float32))
+    f1 = m.triplet_moves(lab, 4, out=np.empty((m.T, 8), np.float32))
+    assert np.array_equal(f1, d[4].astype(np.float32))
+    m.close()
