@@ -404,18 +404,28 @@ def bench_group(args, rank, world, local, metric, unit):
     lab_dev = torch.from_numpy(lab).cuda()
     s0, s1 = sharding.shard_range(S, rank, world)        # whole subjects per rank
     t0, t1 = s0 * T, s1 * T
-    hdl = None
-    if world > 1:
-        import torch.distributed._symmetric_memory as symm_mem
-        full = symm_mem.empty(L * S * T * 8, dtype=torch.float32, device=f"cuda:{local}")
-        hdl = symm_mem.rendezvous(full, dist.group.WORLD)
-        peers = [int(p) for p in hdl.buffer_ptrs]
-        mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if args.cp_exchange == "mc" else 0
-    else:
+    hdl, nccl_gather, why = None, False, ""
+    if world > 1 and args.cp_exchange != "nccl":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            full = symm_mem.empty(L * S * T * 8, dtype=torch.float32, device=f"cuda:{local}")
+            hdl = symm_mem.rendezvous(full, dist.group.WORLD)
+            peers = [int(p) for p in hdl.buffer_ptrs]
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if args.cp_exchange == "mc" else 0
+        except Exception as e:   # no symmetric memory on this box: kernel + NCCL all-gather instead
+            nccl_gather, why = True, f" (p2p unavailable: {type(e).__name__})"
+    elif world > 1:
+        nccl_gather = True
+    if world == 1 or nccl_gather:
         full = torch.empty(L * S * T * 8, dtype=torch.float32, device="cuda")
         peers, mc = [full.data_ptr()], 0
+    d_slice = torch.empty((L, (t1 - t0) * 8), dtype=torch.float32, device="cuda") if nccl_gather else None
 
     def step():
+        if nccl_gather:
+            ctx.triplet_moves_range_dev(lab_dev.data_ptr(), -1, t0, t1, d_slice.data_ptr())
+            full.view(L, S * T * 8).copy_(sharding.allgather_label_major(d_slice, S * T, unit=8).reshape(L, -1))
+            return
         ctx.triplet_moves_range_peers(lab_dev.data_ptr(), -1, t0, t1, peers, mc)
         if hdl is not None:
             hdl.barrier(channel=0)
@@ -462,7 +472,7 @@ def bench_group(args, rank, world, local, metric, unit):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"groupwise (BASELINE.json configs[4]): {S} subjects, ico{lvl} control grids ({N} points, {T} triangles each), "
                                    f"L={L}; step = group fusion-move triplet costs of every label, subjects sharded over {world} GPU(s), table "
-                                   f"assembled on every rank by " + ("NVSwitch multicast stores" if mc else "peer stores") + " (fused exchange)",
+                                   f"assembled on every rank by " + ("an NCCL all-gather" + why if nccl_gather else ("NVSwitch multicast stores" if mc else "peer stores") + " (fused exchange)"),
                        "S": S, "N": N, "T": T, "L": L, "table_bytes": 4 * evals, "max_rel_err_of_sample": checks},
             "gpu_launches": int(ctx.launch_count() - launches0)}))
     ctx.close()
