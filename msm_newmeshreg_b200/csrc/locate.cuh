@@ -6,6 +6,8 @@
 
 namespace msm {
 
+constexpr int kMtabPad = 3;   // leading pad entries of the multiplier table (see msm_set_target)
+
 struct IcoDev {
     int depth;
     int nleaf_per_base;          // 4^depth

@@ -213,7 +213,7 @@ IcoDev ico_dev(const msm_ctx* ctx) {
     d.leaf_off = (d.nleaf_per_base - 1) / 3;
     d.ntab = ctx->d_ntab.as<float4>();
     d.ntab_d = ctx->d_ntab_d.as<double4>();
-    d.mtab = ctx->d_mtab.as<float4>();
+    d.mtab = ctx->d_mtab.as<float4>() + kMtabPad;
     return d;
 }
 
@@ -415,12 +415,14 @@ int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int 
         if (upload(ctx, ctx->d_ntab_d, nd.data(), nd.size())) return 1;
         // child-indexed multiplier table (all nodes of levels 0..depth; node 0 unused)
         const size_t nall = ((size_t(1) << (2 * (H.depth + 1))) - 1) / 3;
-        std::vector<float> mt(nall * 4, 1.f);
+        // stored with kMtabPad leading entries so that the four children of a node (heap ids 4n+1..4n+4) sit in ONE aligned
+        // 64-byte block: a warp's gather then never straddles two 128-byte lines for siblings
+        std::vector<float> mt((nall + kMtabPad) * 4, 1.f);
         for (size_t n = 0; n < H.ntab.size(); n++) {
             const float nab = (float)H.ntab[n][0], nbc = (float)H.ntab[n][1], nca = (float)H.ntab[n][2];
             const float mul[4][3] = {{1.f, nab, nca}, {nab, 1.f, nbc}, {nca, nbc, 1.f}, {nbc, nca, nab}};
             for (int c = 0; c < 4; c++)
-                for (int j = 0; j < 3; j++) mt[(4 * n + 1 + c) * 4 + j] = mul[c][j];
+                for (int j = 0; j < 3; j++) mt[(kMtabPad + 4 * n + 1 + c) * 4 + j] = mul[c][j];
         }
         if (upload(ctx, ctx->d_mtab, mt.data(), mt.size())) return 1;
         CK(cudaStreamSynchronize(ctx->stream));
