@@ -299,6 +299,62 @@ __global__ void __launch_bounds__(1024) k_patch_scan(int n, const int* __restric
     if (tid == 1023) { off[n] = s[1023]; total_max[0] = s[1023]; total_max[1] = s_max; }
 }
 
+// Two-pass exclusive scan for LARGE arrays (the voxel grid's cell counts, up to 64^3): per-chunk sums, then every chunk
+// scans itself on top of the sum of the chunks before it.  Coalesced reads, one CTA per chunk.
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(256) k_scan_chunk_sums(int n, int chunk, const int* __restrict__ counts, int* __restrict__ sums) {
+    __shared__ int s_w[8];
+    const int b = blockIdx.x * chunk, e = min(n, b + chunk);
+    int sum = 0;
+    for (int i = b + threadIdx.x; i < e; i += 256) sum += counts[i];
+    sum = warp_sum_i(sum);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) k_scan_chunk_apply(int n, int chunk, const int* __restrict__ counts, const int* __restrict__ sums,
+                                                          int* __restrict__ off) {
+    __shared__ int s_w[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        int acc = 0;
+        for (int j = lane; j < (int)blockIdx.x; j += 32) acc += sums[j];
+        acc = warp_sum_i(acc);
+        if (lane == 0) s_base = acc;
+    }
+    __syncthreads();
+    int run = s_base;
+    const int b = blockIdx.x * chunk, e = min(n, b + chunk);
+    for (int tile = b; tile < e; tile += 256) {
+        const int i = tile + tid;
+        const int c = i < e ? counts[i] : 0;
+        int inc = c;   // inclusive scan within the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        int before = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { const int t = s_w[w]; if (w < warp) before += t; all += t; }
+        if (i < e) off[i] = run + before + inc - c;
+        run += all;
+        __syncthreads();
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) off[n] = run;
+}
+
 // gather the packed per-patch sample streams (SoA over the global sample index) — coalesced reads in k_unary.
 // Coordinates are stored as offsets from the patch's control point, r = SRC_i - CP_k, formed in fp64: small numbers
 // keep full relative precision in fp32 (absolute coordinates at |x|~100 would not resolve an ico7 triangle to 1e-5).

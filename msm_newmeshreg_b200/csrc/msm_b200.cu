@@ -113,6 +113,7 @@ struct msm_ctx {
     int maxP = 0;
     DevBuf d_counts, d_off, d_idx, d_unc, d_unc_count, d_acc_off, d_acc_idx, d_totmax;
     DevBuf d_px, d_py, d_pz, d_pa, d_pw;
+    DevBuf d_scan_sums;       // chunk sums of the voxel-grid scan
     DevBuf d_vkey;            // [Vs] spatial sort key of every source vertex (k_vertex_key)
     bool vkey_valid = false;
     DevBuf d_cell_counts, d_cell_start, d_cell_fill, d_cell_of, d_sorted;  // voxel grid of the source vertices
@@ -653,9 +654,15 @@ int msm_build_patches(msm_ctx* ctx) {
                 k_bin_count<<<(ctx->Vs + 255) / 256, 256, 0, ctx->stream>>>(bg, ctx->Vs, ctx->d_src.as<double>(), ctx->d_cell_of.as<int>(),
                                                                            ctx->d_cell_counts.as<int>());
                 KLAUNCH_CHECK();
-                k_patch_scan<<<1, 1024, 0, ctx->stream>>>((int)nc, ctx->d_cell_counts.as<int>(), nullptr, ctx->d_cell_start.as<int>(),
-                                                          ctx->d_totmax.as<int>());
-                KLAUNCH_CHECK();
+                {   // exclusive scan of the cell counts: chunk sums, then per-chunk scans (one CTA per chunk)
+                    const int nchunks = 148, chunk = ((int)nc + nchunks - 1) / nchunks;
+                    CK(ctx->d_scan_sums.ensure((size_t)nchunks * 4));
+                    k_scan_chunk_sums<<<nchunks, 256, 0, ctx->stream>>>((int)nc, chunk, ctx->d_cell_counts.as<int>(), ctx->d_scan_sums.as<int>());
+                    KLAUNCH_CHECK();
+                    k_scan_chunk_apply<<<nchunks, 256, 0, ctx->stream>>>((int)nc, chunk, ctx->d_cell_counts.as<int>(), ctx->d_scan_sums.as<int>(),
+                                                                        ctx->d_cell_start.as<int>());
+                    KLAUNCH_CHECK();
+                }
                 k_bin_fill<<<(ctx->Vs + 255) / 256, 256, 0, ctx->stream>>>(bg, ctx->Vs, ctx->d_cell_of.as<int>());
                 KLAUNCH_CHECK();
                 binned = true;
