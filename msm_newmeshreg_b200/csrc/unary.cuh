@@ -239,7 +239,7 @@ __device__ __forceinline__ void unary_items_uni(const UnaryArgs& a, const float*
 }
 
 template <int CQ>
-__global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
+__device__ __forceinline__ void unary_body(const UnaryArgs& a) {
     // padded channel count staged in shared memory; CQ == 5 is the generic variant (any channel count, a.cq_rt quads):
     // source features / weights are then read straight from the packed global streams (coalesced, L1 resident)
     constexpr int CP_ = CQ == 0 ? 1 : (CQ <= 4 ? 4 * CQ : 0);
@@ -433,5 +433,11 @@ __global__ void __launch_bounds__(256) k_unary(UnaryArgs a) {
         }
     }
 }
+
+template <int CQ>
+__global__ void __launch_bounds__(256) k_unary(UnaryArgs a) { unary_body<CQ>(a); }
+// univariate: 6 CTAs per SM (40 registers, no spills) instead of the 5 the default heuristics settle on
+template <>
+__global__ void __launch_bounds__(256, 6) k_unary<0>(UnaryArgs a) { unary_body<0>(a); }
 
 }  // namespace msm
