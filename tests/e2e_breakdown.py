@@ -1,4 +1,5 @@
-"""scratch: e2e per-call breakdown at C3 (ico7 data, ico5 control grid)"""
+"""Per-call breakdown of the end-to-end step at C3 (ico7 data, ico5 control grid) through the host classes; with
+MSM_HOST_TIMING=1 the host library prints its own breakdown.  Not a pytest file:  python tests/e2e_breakdown.py"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
