@@ -24,6 +24,9 @@
 #define HAS_HOCR
 #include "FastPD/FastPD.h"
 #include "Fusion/Fusion.h"
+#ifndef WITH_REF_COST
+#include "src/FusionTables.h"
+#endif
 #endif
 
 using namespace newmeshreg;
@@ -577,6 +580,13 @@ int ref_fusion_model(void* h, int threads, double* energy) {
     auto* b = (ModelBox*)h;
     return guard([&] { *energy = Fusion::optimize(b->model, false, threads); });
 }
+#ifndef WITH_REF_COST
+// the table-aware fusion driver (host/src/FusionTables.h): batched GPU tables in, the reference's ELC / FastPD cores unchanged
+int ref_fusion_tables_model(void* h, int threads, double* energy) {
+    auto* b = (ModelBox*)h;
+    return guard([&] { *energy = FusionTables::optimize(b->model, false, threads); });
+}
+#endif
 int ref_fastpd_tables(int N, int L, int P, const int* pairs, const double* unary, const double* pairtab, int* labeling, double* energy) {
     return guard([&] {
         auto cf = std::make_shared<TableCostFunction>(N, L, P, 0, unary, pairtab, nullptr);

@@ -158,6 +158,16 @@ public:
         sync_device_state();
         check(msm_triplet_moves(ctx, labeling, alpha, out));
     }
+    // batched accessors for a table-aware driver (host/src/FusionTables.h): the pristine unary table [L][N], and the total
+    // energy of a labelling evaluated on the device (src/DiscreteCostFunction.cpp:41-70) without any T*L^3 table
+    const std::vector<double>& unaryTable() { ensure_unary(); return unary_pristine; }
+    double totalCostBatched(const int* labeling) {
+        ensure_unary();
+        sync_device_state();
+        double sums[3] = {0, 0, 0};
+        check(msm_total_cost(ctx, labeling, sums));
+        return sums[0] + sums[1] + sums[2];
+    }
     void computeTripletMoves(const int* labeling, int alpha, float* out) {  // fp32 table: half the read-back
         sync_device_state();
         check(msm_triplet_moves_f32(ctx, labeling, alpha, out));

@@ -96,3 +96,12 @@ def fusion_tables(unary, triplets=None, triptab=None, pairs=None, pairtab=None, 
     if lib().ref_fusion_tables(N, L, P, pp, T, ptr, pu, ppt, ptt, threads, lab.ctypes.data_as(c_ip), C.byref(e)) != 0:
         raise RuntimeError(lib().msmhost_last_error().decode())
     return lab, e.value
+
+
+def fusion_tables_model(m, threads=1):
+    """The product's table-aware fusion driver (msm_newmeshreg_b200/host/src/FusionTables.h: batched GPU tables feeding
+    the reference's ELC / FastPD cores) on the GPU-backed model `m`; same return convention as fusion_model."""
+    e = C.c_double()
+    if lib().ref_fusion_tables_model(m.h, threads, C.byref(e)) != 0:
+        raise RuntimeError(lib().msmhost_last_error().decode())
+    return m.labeling(), e.value

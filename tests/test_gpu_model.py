@@ -210,3 +210,21 @@ def test_triplet_moves_fp32_variant_is_the_rounded_fp64_table(built):
     f1 = m.triplet_moves(lab, 4, out=np.empty((m.T, 8), np.float32))
     assert np.array_equal(f1, d[4].astype(np.float32))
     m.close()
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("C", [1, 4])
+def test_table_aware_fusion_driver_equals_fusion_optimize(built, C):
+    """host/src/FusionTables.h (batched move tables, no T*L^3 table, no per-element virtuals) against the reference's
+    unmodified Fusion::optimize on the same GPU-backed model: same labelling, same energy."""
+    P = pb.make_problem(4, 2, C, seed=91, warp=0.3, deform_cp=0.1)
+    labs, ens = [], []
+    for driver in (pyref.fusion_model, pyref.fusion_tables_model):
+        m = _model(P, lib=pyref.lib(), rmode=3, dopt="HOCR")
+        m.reset_cpgrid(P.cxyz); m.setup()
+        lab, e = driver(m, threads=4)
+        labs.append(lab.copy()); ens.append(e)
+        m.close()
+    assert np.array_equal(labs[0], labs[1]), f"{(labs[0] != labs[1]).sum()} of {P.N} labels differ"
+    assert abs(ens[0] - ens[1]) <= 1e-6 * abs(ens[0])
+    assert len(np.unique(labs[0])) > 1
