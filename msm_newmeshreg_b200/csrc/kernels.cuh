@@ -557,7 +557,26 @@ __global__ void __launch_bounds__(128) k_triplet_queries(TripArgs a, int n, cons
 
 // fusion-move costs (include/Fusion/Fusion.h:187-194): combo bit2->A, bit1->B, bit0->C take label alpha.
 // alpha >= 0: out[t][8]; alpha < 0: all labels, out[alpha][t][8].
-template <typename OutT>
+// The default configuration (strain regulariser with k = 2 and exponent 2, or the group rules with exponent 2) without the
+// angular mode, pow() and the other rarely used branches: a fraction of the code and registers of trip_cost.  Same
+// arithmetic as trip_cost for those parameters.
+__device__ __forceinline__ double trip_cost_fast(const DevParams& p, const TripGeom& g, const double* d0, const double* d1, const double* d2) {
+    double e1[3], e2[3], nn[3];
+    for (int j = 0; j < 3; j++) { e1[j] = d1[j] - d0[j]; e2[j] = d2[j] - d0[j]; }
+    cross3(e1, e2, nn);
+    const bool fold = dot3(nn, g.n) < 0.0;
+    const double W = strain_energy(dot3(e1, e1), dot3(e1, e2), dot3(e2, e2), g, p.mu, p.kappa, 2.0);
+    if (p.group) return fold ? 1e7 : p.lambda * (W * W);
+    double cost = fold ? 1.0 : W;
+    const double weight = fold ? 1.0 + 1e6 : 1.0;
+    if (fabs(cost) < 1e-8) cost = 0.0;
+    return weight * p.lambda * (cost * cost);
+}
+__host__ __device__ inline bool trip_fast_ok(const DevParams& p) {
+    return p.rexp == 2.0 && (p.group || (p.rmode == 3 && p.k_exp == 2.0));
+}
+
+template <typename OutT, bool FAST>
 __global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const int* __restrict__ labeling, int alpha, OutT* __restrict__ out,
                                                        PeerSet peers = PeerSet{}, int t_full = 0) {
     // one thread per (alpha, triplet): the triangle constants and the six candidate corners (current / alpha label of
@@ -581,7 +600,10 @@ __global__ void __launch_bounds__(128) k_triplet_moves(TripArgs a, int T, const 
     OutT* o = peers.world > 0 ? nullptr : out + gid * 8;
 #pragma unroll
     for (int combo = 0; combo < 8; combo++) {
-        const OutT v = (OutT)trip_cost(a.p, g, (combo & 4) ? pa[0] : pc[0], (combo & 2) ? pa[1] : pc[1], (combo & 1) ? pa[2] : pc[2]);
+        const double* d0 = (combo & 4) ? pa[0] : pc[0];
+        const double* d1 = (combo & 2) ? pa[1] : pc[1];
+        const double* d2 = (combo & 1) ? pa[2] : pc[2];
+        const OutT v = (OutT)(FAST ? trip_cost_fast(a.p, g, d0, d1, d2) : trip_cost(a.p, g, d0, d1, d2));
         if (o) o[combo] = v;
         (&(combo < 4 ? lo : hi).x)[combo & 3] = (float)v;
     }

@@ -961,6 +961,13 @@ int msm_triplet_table(msm_ctx* ctx, int t0, int t1, float* out) {
     return 0;
 }
 
+// picks the lean kernel for the default regulariser settings (kernels.cuh trip_cost_fast)
+#define LAUNCH_TRIPLET_MOVES(OUT_T, grid, ...)                                                       \
+    do {                                                                                             \
+        if (trip_fast_ok(dev_params(ctx))) k_triplet_moves<OUT_T, true><<<(grid), 128, 0, ctx->stream>>>(__VA_ARGS__);  \
+        else k_triplet_moves<OUT_T, false><<<(grid), 128, 0, ctx->stream>>>(__VA_ARGS__);             \
+    } while (0)
+
 int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, float* d_out) {
     CK(cudaSetDevice(ctx->device));
     if (check_triplets(ctx)) return 1;
@@ -971,7 +978,7 @@ int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, 
     TripArgs a = trip_args(ctx);
     a.t_off = t0;
     Timer tm(ctx, "triplet_moves");
-    k_triplet_moves<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, t1 - t0, d_labeling, alpha, d_out);
+    LAUNCH_TRIPLET_MOVES(float, (unsigned)((n + 127) / 128), a, t1 - t0, d_labeling, alpha, d_out);
     KLAUNCH_CHECK();
     return 0;
 }
@@ -989,7 +996,7 @@ int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha
     TripArgs a = trip_args(ctx);
     a.t_off = t0;
     Timer tm(ctx, "triplet_moves");
-    k_triplet_moves<float><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, t1 - t0, d_labeling, alpha, nullptr, ps, ctx->Tn);
+    LAUNCH_TRIPLET_MOVES(float, (unsigned)((n + 127) / 128), a, t1 - t0, d_labeling, alpha, (float*)nullptr, ps, ctx->Tn);
     KLAUNCH_CHECK();
     return 0;
 }
@@ -1010,8 +1017,7 @@ int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out)
     CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timer tm(ctx, "triplet_moves");
-        k_triplet_moves<double><<<(unsigned)((n / 8 + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha,
-                                                                                   ctx->d_scratch2.as<double>());
+        LAUNCH_TRIPLET_MOVES(double, (unsigned)((n / 8 + 127) / 128), trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha, ctx->d_scratch2.as<double>());
         KLAUNCH_CHECK();
     }
     CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1032,8 +1038,7 @@ int msm_triplet_moves_f32(msm_ctx* ctx, const int* labeling, int alpha, float* o
     CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timer tm(ctx, "triplet_moves");
-        k_triplet_moves<float><<<(unsigned)((n / 8 + 127) / 128), 128, 0, ctx->stream>>>(trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha,
-                                                                                  ctx->d_scratch2.as<float>());
+        LAUNCH_TRIPLET_MOVES(float, (unsigned)((n / 8 + 127) / 128), trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha, ctx->d_scratch2.as<float>());
         KLAUNCH_CHECK();
     }
     CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
