@@ -132,9 +132,9 @@ public:
     void set_coord(int i, const Point& p) { Vw()[i] = p; }
     // all vertices at once from a flat [nv][3] array: one bulk copy into storage of its own (other copies keep theirs)
     void set_coords(const double* xyz) {
-        auto n = std::make_shared<std::vector<Point>>(V().size());
-        if (!n->empty()) std::memcpy(static_cast<void*>(n->data()), xyz, n->size() * sizeof(Point));
-        V_ = std::move(n);
+        static_assert(sizeof(Point) == 3 * sizeof(double), "Point must be three packed doubles");
+        const Point* first = reinterpret_cast<const Point*>(xyz);
+        V_ = std::make_shared<std::vector<Point>>(first, first + V().size());   // one pass, no zero fill
     }
     int get_triangle_vertexID(int t, int j) const { return topo_->F[t][j]; }
     Point get_triangle_vertex(int t, int j) const { return V()[topo_->F[t][j]]; }
