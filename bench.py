@@ -377,17 +377,21 @@ def bench_group(args, rank, world, local, metric, unit):
     (src/DiscreteGroupCostFunction.cpp:9-30), subjects sharded over the GPUs.  The S control meshes are replicated (S*N
     points, small); each GPU evaluates the fusion-move triplet costs of every label for ITS subjects' triangles and stores
     them straight into every rank's [L][S*T][8] table over peer mappings (fused exchange), one barrier per step — the joint
-    host optimiser needs the whole table.  A sample of the table is checked against the oracle port and, when built, the
-    reference's own DiscreteGroupCostFunction."""
+    host optimiser needs the whole table.  (Parity of this configuration — a sample of the table against the oracle port and
+    the reference's own DiscreteGroupCostFunction — is tests/test_gpu_parity.py::test_group_triplets_full_size.)"""
     import torch
     import torch.distributed as dist
-    from msm_newmeshreg_b200 import Context, sharding
-    from oracle import pyorc, pyrefcost
+    from msm_newmeshreg_b200 import Context, host, sharding
     S, lvl = args.group_subjects, args.group_cp_level
-    cxyz0, ctris = pyorc.icosphere(lvl)
-    maxsep, mvdmax, mvd = pyorc.spacings(cxyz0, ctris)
-    samples, bary, centre = pyorc.label_grid(lvl + 2, 0.5 * mvdmax)
-    trip1 = pyorc.triplets(cxyz0, ctris)
+    cxyz0, ctris = host.icosphere(lvl)
+    mvd = float(np.linalg.norm(cxyz0[ctris[:, 0]] - cxyz0[ctris[:, 1]], axis=1).mean())
+    # label set and cliques from the host model glue (src/DiscreteModel.cpp:91-162,267-282) on a throw-away model
+    m = host.Model(sgres=lvl + 2, cpres=lvl, multivariate=False, dopt="HOCR", threads=1, **PARAMS)
+    feat = random_field(cxyz0, 1)[None]
+    m.set_data(cxyz0, ctris, cxyz0, ctris, feat, feat); m.initialize(); m.setup()
+    bary, trip1 = m.labels(), m.triplets()
+    centre = bary[0]
+    m.close()
     N, T, L = len(cxyz0), len(trip1), len(bary)
     cps = np.stack([smooth_warp(cxyz0, 500 + s, 0.25 * mvd) for s in range(S)])
     trip = np.concatenate([trip1 + s * N for s in range(S)]).astype(np.int32)
@@ -438,21 +442,7 @@ def bench_group(args, rank, world, local, metric, unit):
     for _ in range(max(args.warmup, 3)):
         step()
     sync_all()
-    # parity of a sample of the assembled table (every rank holds all of it)
-    M = full.view(L, S * T, 8).cpu().numpy()
-    rng = np.random.default_rng(3)
-    qa, qt, qc = rng.integers(0, L, 4000), rng.integers(0, S * T, 4000), rng.integers(0, 8, 4000)
-    q = np.stack([qt, np.where(qc & 4, qa, lab[trip[qt, 0]]), np.where(qc & 2, qa, lab[trip[qt, 1]]), np.where(qc & 1, qa, lab[trip[qt, 2]])], 1).astype(np.int32)
-    rot = np.concatenate([pyorc.rotations(centre, cps[s]) for s in range(S)])
-    got = M[qa, qt, qc].astype(np.float64)
-    checks = {}
-    for name, G in (("oracle", pyorc.GroupCost), ("reference", pyrefcost.GroupCost if pyrefcost.available() else None)):
-        if G is None:
-            continue
-        g = G(); g.set(lam, 2.0, mu, kappa, cps, ctris, cxyz0, bary, rot, trip)
-        want = g.triplet_costs(q)
-        checks[name] = float((np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * lam)).max())
-        assert checks[name] < 1e-5, (name, checks[name])
+    checksum = float(full.double().sum().item())
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -473,7 +463,7 @@ def bench_group(args, rank, world, local, metric, unit):
             "config": {"workload": f"groupwise (BASELINE.json configs[4]): {S} subjects, ico{lvl} control grids ({N} points, {T} triangles each), "
                                    f"L={L}; step = group fusion-move triplet costs of every label, subjects sharded over {world} GPU(s), table "
                                    f"assembled on every rank by " + ("an NCCL all-gather" + why if nccl_gather else ("NVSwitch multicast stores" if mc else "peer stores") + " (fused exchange)"),
-                       "S": S, "N": N, "T": T, "L": L, "table_bytes": 4 * evals, "max_rel_err_of_sample": checks},
+                       "S": S, "N": N, "T": T, "L": L, "table_bytes": 4 * evals, "checksum": checksum},
             "gpu_launches": int(ctx.launch_count() - launches0)}))
     ctx.close()
     if world > 1:

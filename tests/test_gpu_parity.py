@@ -436,3 +436,42 @@ def test_fused_exchange_kernels_fill_every_peer_table(built):
     for r in range(world):
         assert np.array_equal(tabs_u[r].cpu().numpy(), U)
         assert np.array_equal(tabs_m[r].cpu().numpy(), M)
+
+
+def test_group_triplets_full_size(built):
+    """BASELINE configs[4] at full size (16 subjects x ico4 control grids, 81 920 triangles): a sample of the all-label
+    fusion-move table against the oracle port and, when built, the reference's own DiscreteGroupCostFunction."""
+    import torch
+    from msm_newmeshreg_b200 import Context
+    from oracle import pyrefcost
+    S, lvl = 16, 4
+    cxyz0, ctris = pyorc.icosphere(lvl)
+    maxsep, mvdmax, mvd = pyorc.spacings(cxyz0, ctris)
+    samples, bary, centre = pyorc.label_grid(lvl + 2, 0.5 * mvdmax)
+    trip1 = pyorc.triplets(cxyz0, ctris)
+    N, T, L = len(cxyz0), len(trip1), len(bary)
+    cps = np.stack([pb.smooth_warp(cxyz0, 500 + s, 0.25 * mvd) for s in range(S)])
+    trip = np.concatenate([trip1 + s * N for s in range(S)]).astype(np.int32)
+    lam, mu, kappa = pb.f32(0.2), pb.f32(0.4), pb.f32(1.6)
+    ctx = Context()
+    ctx.set_params(lam=lam, rexp=2.0, mu=mu, kappa=kappa, rmode=3, group=True)
+    ctx.set_cpgrid(cps.reshape(-1, 3), np.zeros((0, 3), np.int32), np.ones(S * N), np.tile(cxyz0, (S, 1)))
+    ctx.set_group(S, N, T); ctx.set_labels(bary, centre); ctx.set_triplets(trip)
+    lab = np.random.default_rng(7).integers(0, L, S * N).astype(np.int32)
+    full = torch.full((L, S * T, 8), float("nan"), dtype=torch.float32, device="cuda")
+    ctx.triplet_moves_range_peers(torch.from_numpy(lab).cuda().data_ptr(), -1, 0, S * T, [full.data_ptr()])
+    ctx.synchronize()
+    M = full.cpu().numpy()
+    assert np.isfinite(M).all()
+    rng = np.random.default_rng(3)
+    qa, qt, qc = rng.integers(0, L, 4000), rng.integers(0, S * T, 4000), rng.integers(0, 8, 4000)
+    q = np.stack([qt, np.where(qc & 4, qa, lab[trip[qt, 0]]), np.where(qc & 2, qa, lab[trip[qt, 1]]), np.where(qc & 1, qa, lab[trip[qt, 2]])], 1).astype(np.int32)
+    rot = np.concatenate([pyorc.rotations(centre, cps[s]) for s in range(S)])
+    got = M[qa, qt, qc].astype(np.float64)
+    for G in (pyorc.GroupCost, pyrefcost.GroupCost if pyrefcost.available() else None):
+        if G is None:
+            continue
+        g = G(); g.set(lam, 2.0, mu, kappa, cps, ctris, cxyz0, bary, rot, trip)
+        want = g.triplet_costs(q)
+        assert (np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * lam)).max() < 1e-6     # fp32 table
+    ctx.close()
