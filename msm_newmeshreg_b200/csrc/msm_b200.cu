@@ -263,7 +263,7 @@ int choose_hint_level(const msm_ctx* ctx) {
     const double disc = ctx->par.range * maxsep + ctx->max_label_disp;
     const double edge0 = 110.71487177940904;  // icosahedron edge arc length at R = 100
     int h = 0;
-    while (h + 1 < depth && edge0 / double(1 << (h + 1)) > 3.0 * disc) h++;
+    while (h + 1 < depth && edge0 / double(1 << (h + 1)) > 2.0 * disc) h++;
     return h;
 }
 
