@@ -475,3 +475,23 @@ def test_group_triplets_full_size(built):
         want = g.triplet_costs(q)
         assert (np.abs(got - want) / np.maximum(np.abs(want), 1e-3 * lam)).max() < 1e-6     # fp32 table
     ctx.close()
+
+
+def test_fused_exchange_argument_errors(built):
+    import torch
+    from msm_newmeshreg_b200 import MsmError
+    P = pb.make_problem(3, 2, 1, seed=8, warp=0.2)
+    ctx = pb.gpu_context(P); ctx.build_patches()
+    buf = torch.zeros((P.L, P.N), dtype=torch.float32, device="cuda")
+    with pytest.raises(MsmError, match="world size"):
+        ctx.unary_table_peers([])
+    with pytest.raises(MsmError, match="world size"):
+        ctx.unary_table_peers([buf.data_ptr()] * 17)
+    with pytest.raises(MsmError, match="null peer"):
+        ctx.unary_table_peers([buf.data_ptr(), 0])
+    lab = torch.zeros(P.N, dtype=torch.int32, device="cuda")
+    with pytest.raises(MsmError, match="bad triplet range"):
+        ctx.triplet_moves_range_peers(lab.data_ptr(), -1, 5, P.T + 1, [buf.data_ptr()])
+    ctx.unary_table_peers([buf.data_ptr()]); ctx.synchronize()          # still usable after the errors
+    assert np.array_equal(buf.cpu().numpy().astype(np.float64), ctx.unary_table())
+    ctx.close()
