@@ -13,7 +13,9 @@ state exceed the 126 MB L2, so successive timed iterations do not find their inp
 
   value : evaluations / second, inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks.
   e2e   : the same step through the reference-facing host classes (NonLinearSRegDiscreteModel::reset_meshspace ->
-          setupCostFunction [patch construction + unary table] -> triplet moves) with pinned HOST buffers in and out.
+          setupCostFunction [patch construction + unary table] -> triplet moves) with pinned HOST buffers in and out;
+          the B independent subjects of a GPU are driven by --e2e-threads host threads, one private stream each
+          (e2e.value_one_host_thread = the same with a serial loop).
   --impl reference : THE REFERENCE'S OWN cost-function classes (oracle/_ref/libref_cost.so: its sources compiled in place
           over stand-ins for the absent FSL libraries) on the host cores, bounded sample of the same workload; falls back
           to the oracle port (kind "port") only if that library was not built.
@@ -482,6 +484,7 @@ def main():
     ap.add_argument("--cp-level", type=int, default=5)
     ap.add_argument("--channels", type=int, default=1)
     ap.add_argument("--cpu-rows", type=int, default=1024, help="control points in the bounded CPU sample")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the subjects of one GPU in the e2e leg")
     ap.add_argument("--mode", default="subjects", choices=["subjects", "cp", "group"],
                     help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
                          "and triplets sharded over the GPUs (strong scaling); group: groupwise registration "
@@ -627,31 +630,54 @@ def main():
     value = evals_per_subject * B * world / (ms_per_step * 1e-3)
 
     # ---- end to end through the host classes, host buffers in/out
-    def e2e_step():
-        for s in range(B):
-            sx, cx = host_bufs[s]
-            models[s].reset_meshspace(sx.numpy())
-            models[s].reset_cpgrid(cx.numpy())
-            models[s].setup()                       # patch construction + unary table -> host double[L][N]
-            models[s].triplet_moves(lab_host, -1, out=moves_host.numpy())   # -> pinned host float[L][T][8] (fp32 table)
+    # The B subjects of a GPU are independent registrations: each one is driven by its own host thread on its context's
+    # private stream, so one subject's uploads, kernels, read-backs and host-side mesh copies overlap the others'
+    # (PCIe is full duplex; ctypes releases the GIL inside the host library).  --e2e-threads 1 is the serial loop.
+    def subject_step(s):
+        sx, cx = host_bufs[s]
+        models[s].reset_meshspace(sx.numpy())
+        models[s].reset_cpgrid(cx.numpy())
+        models[s].setup()                       # patch construction + unary table -> host double[L][N]
+        models[s].triplet_moves(lab_host, -1, out=moves_host[s].numpy())   # -> pinned host float[L][T][8] (fp32 table)
 
-    moves_host = torch.empty((L, T, 8), dtype=torch.float32).pin_memory()
-    for _ in range(1):
-        e2e_step()
-    sync_all()
-    k_e2e = max(1, min(args.steps, 5))
-    reps = []
-    for _ in range(3):   # host-side timing is noisy: median of three repetitions of k_e2e steps
-        t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        reps.append((time.perf_counter() - t0) / k_e2e)
-    dt = sorted(reps)[1]
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = evals_per_subject * B * world / float(t.item())
+    for c in ctxs:
+        c.set_stream(0)                         # back to the context's own stream
+    moves_host = [torch.empty((L, T, 8), dtype=torch.float32).pin_memory() for _ in range(B)]
+    k_e2e = max(1, min(args.steps, 10))
+
+    def time_e2e(nthreads):
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(nthreads) if nthreads > 1 else None
+
+        def subject_steps(s, k):
+            for _ in range(k):
+                subject_step(s)
+
+        def e2e_steps(k):     # k steps of every subject; no barrier between the steps of different subjects
+            if pool:
+                list(pool.map(lambda s: subject_steps(s, k), range(B)))
+            else:
+                for _ in range(k):
+                    for s in range(B):
+                        subject_step(s)
+        e2e_steps(1)
+        sync_all()
+        reps = []
+        for _ in range(3):   # host-side timing is noisy: median of three repetitions of k_e2e steps
+            t0 = time.perf_counter()
+            e2e_steps(k_e2e)
+            torch.cuda.synchronize()
+            reps.append((time.perf_counter() - t0) / k_e2e)
+        if pool:
+            pool.shutdown()
+        t = torch.tensor([sorted(reps)[1]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return evals_per_subject * B * world / float(t.item())
+
+    e2e_threads = max(1, min(B, args.e2e_threads))
+    e2e_serial = time_e2e(1)
+    e2e_value = time_e2e(e2e_threads) if e2e_threads > 1 else e2e_serial
     Vs = len(txyz)
     h2d = B * (Vs * 24 + N * 24 + N * 4)
     d2h = B * (L * N * 4 + L * T * 8 * 4)
@@ -682,6 +708,7 @@ def main():
                          "algorithmic_bytes_per_launch": float(np.mean(alg_bytes_unary)), "avg_launch_ms": unary_ms, "launches_timed": un,
                          "triplet_moves_avg_ms": tm_ / max(tn_, 1)},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e,
+                    "host_threads": e2e_threads, "value_one_host_thread": e2e_serial,
                     "api": "NonLinearSRegDiscreteModel::reset_meshspace/reset_CPgrid/setupCostFunction + computeTripletMoves"},
             "gpu_launches": int(launches), "clocks": clocks,
         }

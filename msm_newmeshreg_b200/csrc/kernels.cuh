@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(256) k_locate(IcoDev ico, int M, const double*
     if (i >= M) return;
     double al, be, ga;
     const double px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
-    const int hint = ico_base_face<double>(px, py, pz);
+    const int hint = ico_base_face<double>(ico, px, py, pz);
     const int leaf = ico_locate<double>(ico, hint, px, py, pz, al, be, ga);
     const double inv = 1.0 / (al + be + ga);
     const double wl[3] = {al * inv, be * inv, ga * inv};

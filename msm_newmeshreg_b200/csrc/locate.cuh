@@ -8,7 +8,16 @@ namespace msm {
 
 constexpr int kMtabPad = 3;   // leading pad entries of the multiplier table (see msm_set_target)
 
+// 20 base faces: dual basis rows (alpha = A.p, beta = B.p, gamma = C.p) and centre directions.
+struct IcoBase {
+    float dual[20][9];
+    float centre[20][3];
+    double dual_d[20][9];
+    double centre_d[20][3];
+};
+
 struct IcoDev {
+    const IcoBase* base;         // device memory, one per context: contexts over differently oriented spheres coexist
     int depth;
     int nleaf_per_base;          // 4^depth
     int leaf_off;                // (4^depth - 1)/3 : heap index of the first leaf-level node
@@ -47,15 +56,6 @@ __device__ __forceinline__ void multicast_store(float4* addr, const float4& v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// 20 base faces: dual basis rows (alpha = A.p, beta = B.p, gamma = C.p) and centre directions.
-struct IcoBase {
-    float dual[20][9];
-    float centre[20][3];
-    double dual_d[20][9];
-    double centre_d[20][3];
-};
-__constant__ IcoBase c_ico_base;
-
 template <typename T> struct NodeN;
 template <> struct NodeN<float> {
     static __device__ __forceinline__ void load(const IcoDev& ico, int n, float& nab, float& nbc, float& nca) {
@@ -70,21 +70,21 @@ template <> struct NodeN<double> {
     }
 };
 
-template <typename T> __device__ __forceinline__ const T* base_dual(int b);
-template <> __device__ __forceinline__ const float* base_dual<float>(int b) { return c_ico_base.dual[b]; }
-template <> __device__ __forceinline__ const double* base_dual<double>(int b) { return c_ico_base.dual_d[b]; }
-template <typename T> __device__ __forceinline__ const T* base_centre(int b);
-template <> __device__ __forceinline__ const float* base_centre<float>(int b) { return c_ico_base.centre[b]; }
-template <> __device__ __forceinline__ const double* base_centre<double>(int b) { return c_ico_base.centre_d[b]; }
+template <typename T> __device__ __forceinline__ const T* base_dual(const IcoDev& ico, int b);
+template <> __device__ __forceinline__ const float* base_dual<float>(const IcoDev& ico, int b) { return ico.base->dual[b]; }
+template <> __device__ __forceinline__ const double* base_dual<double>(const IcoDev& ico, int b) { return ico.base->dual_d[b]; }
+template <typename T> __device__ __forceinline__ const T* base_centre(const IcoDev& ico, int b);
+template <> __device__ __forceinline__ const float* base_centre<float>(const IcoDev& ico, int b) { return ico.base->centre[b]; }
+template <> __device__ __forceinline__ const double* base_centre<double>(const IcoDev& ico, int b) { return ico.base->centre_d[b]; }
 
 // Base face containing p: the face cones of a regular icosahedron are the Voronoi cells of the face centres.
 template <typename T>
-__device__ __forceinline__ int ico_base_face(T px, T py, T pz) {
+__device__ __forceinline__ int ico_base_face(const IcoDev& ico, T px, T py, T pz) {
     int best = 0;
     T bv = -1e30f;
 #pragma unroll
     for (int b = 0; b < 20; b++) {
-        const T* c = base_centre<T>(b);
+        const T* c = base_centre<T>(ico, b);
         T v = px * c[0] + py * c[1] + pz * c[2];
         if (v > bv) { bv = v; best = b; }
     }
@@ -183,13 +183,13 @@ __device__ __forceinline__ int ico_walk(const HintDev& hd, int face, float& al, 
 template <typename T>
 __device__ __forceinline__ int ico_locate(const IcoDev& ico, int hint_base, T px, T py, T pz, T& al, T& be, T& ga) {
     int base = hint_base;
-    const T* d = base_dual<T>(base);
+    const T* d = base_dual<T>(ico, base);
     al = d[0] * px + d[1] * py + d[2] * pz;
     be = d[3] * px + d[4] * py + d[5] * pz;
     ga = d[6] * px + d[7] * py + d[8] * pz;
     if (fminf(float(al), fminf(float(be), float(ga))) < 0.f) {
-        base = ico_base_face<T>(px, py, pz);
-        d = base_dual<T>(base);
+        base = ico_base_face<T>(ico, px, py, pz);
+        d = base_dual<T>(ico, base);
         al = d[0] * px + d[1] * py + d[2] * pz;
         be = d[3] * px + d[4] * py + d[5] * pz;
         ga = d[6] * px + d[7] * py + d[8] * pz;

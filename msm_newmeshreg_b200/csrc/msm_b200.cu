@@ -75,7 +75,7 @@ struct msm_ctx {
     IcoHierarchy ico;
     bool have_target = false;
     int Vt = 0, Ft = 0, Ct = 0;
-    DevBuf d_ntab, d_ntab_d, d_mtab, d_leaf_vid, d_leaf_user, d_leaf_perm, d_tfeat, d_face_feat;
+    DevBuf d_ico_base, d_ntab, d_ntab_d, d_mtab, d_leaf_vid, d_leaf_user, d_leaf_perm, d_tfeat, d_face_feat;
     int face_feat_cq = -1;  // layout the face-packed features were built for (-1 none, 0 univariate, q quads)
     int hint_level = -1;    // level the hint tables below were built for
     DevBuf d_hdual, d_hnbr, d_hT;
@@ -209,6 +209,7 @@ int upload_as_float(msm_ctx* ctx, DevBuf& b, const double* h, size_t n) {
 
 IcoDev ico_dev(const msm_ctx* ctx) {
     IcoDev d;
+    d.base = ctx->d_ico_base.as<IcoBase>();
     d.depth = ctx->ico.depth;
     d.nleaf_per_base = 1 << (2 * ctx->ico.depth);
     d.leaf_off = (d.nleaf_per_base - 1) / 3;
@@ -429,12 +430,13 @@ int msm_set_target(msm_ctx* ctx, const double* xyz, int V, const int* tris, int 
         CK(cudaStreamSynchronize(ctx->stream));
     }
     {
-        static IcoBase hb;  // ~3.4 KB
+        IcoBase hb;  // ~3.4 KB, per context (a process-wide __constant__ would be shared by every context of the device)
         for (int b = 0; b < 20; b++) {
             for (int j = 0; j < 9; j++) { hb.dual[b][j] = (float)H.dual[b][j]; hb.dual_d[b][j] = H.dual[b][j]; }
             for (int j = 0; j < 3; j++) { hb.centre[b][j] = (float)H.centre[b][j]; hb.centre_d[b][j] = H.centre[b][j]; }
         }
-        CK(cudaMemcpyToSymbol(c_ico_base, &hb, sizeof(IcoBase)));
+        if (upload(ctx, ctx->d_ico_base, &hb, 1)) return 1;
+        CK(cudaStreamSynchronize(ctx->stream));
     }
     {
         std::vector<int> lv((size_t)F * 3);

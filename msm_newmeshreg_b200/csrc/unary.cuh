@@ -24,8 +24,8 @@ namespace msm {
 // fp64 descent of a point from its base face: `nlev` levels; returns base face, heap node, corner coordinates
 __device__ __forceinline__ void descend_d(const IcoDev& ico, int nlev, double px, double py, double pz, int& base, int& n, double& al,
                                           double& be, double& ga) {
-    base = ico_base_face<double>(px, py, pz);
-    const double* d = c_ico_base.dual_d[base];
+    base = ico_base_face<double>(ico, px, py, pz);
+    const double* d = base_dual<double>(ico, base);
     al = d[0] * px + d[1] * py + d[2] * pz; be = d[3] * px + d[4] * py + d[5] * pz; ga = d[6] * px + d[7] * py + d[8] * pz;
     n = 0;
     for (int l = 0; l < nlev; l++) {

@@ -153,6 +153,32 @@ def test_target_numbering_and_orientation_independent(built):
         pb.gpu_context(bad)
 
 
+def test_contexts_over_differently_oriented_targets_coexist(built):
+    """The base-icosahedron frames are per-context state: a second live context over a rotated target sphere does not
+    disturb the first one (and vice versa)."""
+    P = pb.make_problem(4, 2, 1, seed=4, warp=0.3)
+    a = pb.gpu_context(P); a.build_patches(); U0 = a.unary_table()
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0.0], [np.sin(th), np.cos(th), 0.0], [0.0, 0.0, 1.0]]) @ \
+        np.array([[1.0, 0.0, 0.0], [0.0, np.cos(0.4), -np.sin(0.4)], [0.0, np.sin(0.4), np.cos(0.4)]])
+    Q = pb.make_problem(4, 2, 1, seed=4, warp=0.3)
+    Q.txyz = P.txyz @ R.T
+    b = pb.gpu_context(Q); b.build_patches(); Ub = b.unary_table()
+    assert np.array_equal(a.unary_table(), U0)
+    xyz = P.sxyz[:500]
+    ta, wa = a.locate(xyz)
+    a.close()
+    assert np.array_equal(b.unary_table(), Ub)
+    b.close()
+    c = pb.gpu_context(Q); c.build_patches()
+    assert np.array_equal(c.unary_table(), Ub)
+    c.close()
+    d = pb.gpu_context(P)
+    td, wd = d.locate(xyz)
+    assert np.array_equal(ta, td) and np.array_equal(wa, wd)
+    d.close()
+
+
 def test_shards_equal_single_context(built):
     """CP sharding: rows of the sharded tables are bit-identical to the single-context table."""
     from msm_newmeshreg_b200 import sharding as sh
