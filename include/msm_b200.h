@@ -5,8 +5,10 @@
  * mirror of the reference classes (msm_newmeshreg_b200/host/) is a thin layer over these calls.
  *
  * Conventions
- *  - All host arrays are caller-owned; the context owns every device buffer.  One context per GPU; a context
- *    is NOT thread-safe (one host thread drives it), table look-ups on the host side are.
+ *  - All host arrays are caller-owned; the context owns every device buffer.  A context is NOT thread-safe (one
+ *    host thread at a time drives it), table look-ups on the host side are.  DIFFERENT contexts share no mutable
+ *    state and every call selects its context's device, so they may be driven concurrently from different
+ *    threads — several per GPU (independent subjects, each on its own stream) or one per GPU.
  *  - Coordinates are double[n][3] on the sphere of radius 100 (RAD, src/DiscreteCostFunction.h:9).
  *  - Feature matrices are channel-major double[C][V], i.e. FEAT->get_ref_val(d+1, v+1) == ref[d*V + v]
  *    (src/featurespace.h:30-32).

@@ -22,7 +22,7 @@ using namespace msm;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;   // per thread: contexts may be created concurrently
 
 struct DevBuf {
     void* p = nullptr;
@@ -385,11 +385,12 @@ void msm_destroy(msm_ctx* ctx) {
 const char* msm_last_error(const msm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int msm_set_stream(msm_ctx* ctx, void* s) {
+    CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return 0;
 }
-int msm_synchronize(msm_ctx* ctx) { CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+int msm_synchronize(msm_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
 
 int msm_set_params(msm_ctx* ctx, const msm_params* p) {
     if (p->bary_orthogonal) FAIL("bary_orthogonal: only the radial projection (A4 default) is implemented on the device");

@@ -179,6 +179,32 @@ def test_contexts_over_differently_oriented_targets_coexist(built):
     d.close()
 
 
+def test_contexts_driven_from_concurrent_host_threads(built):
+    """Independent subjects, one context and one host thread each (bench.py's end-to-end leg): the tables are
+    bit-identical to the ones a single thread gets one subject at a time."""
+    from concurrent.futures import ThreadPoolExecutor
+    probs = [pb.make_problem(5, 3, 1, seed=20 + s, warp=0.3, deform_cp=0.1) for s in range(4)]
+    q = np.array([[t, (t * 7) % probs[0].L, (t * 3 + 1) % probs[0].L, (t * 5 + 2) % probs[0].L] for t in range(probs[0].T)], np.int32)
+
+    def run(P, reps):
+        ctx = pb.gpu_context(P)
+        out = None
+        for _ in range(reps):
+            ctx.reset_source(P.sxyz); ctx.reset_cpgrid(P.cxyz)
+            ctx.build_patches()
+            cur = (ctx.unary_table(), ctx.triplet_costs(q), ctx.patches()[1])
+            assert out is None or all(np.array_equal(a, b) for a, b in zip(out, cur))
+            out = cur
+        ctx.close()
+        return out
+
+    serial = [run(P, 1) for P in probs]
+    with ThreadPoolExecutor(4) as pool:
+        threaded = list(pool.map(lambda P: run(P, 5), probs))
+    for a, b in zip(serial, threaded):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_shards_equal_single_context(built):
     """CP sharding: rows of the sharded tables are bit-identical to the single-context table."""
     from msm_newmeshreg_b200 import sharding as sh
