@@ -479,12 +479,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--subjects-per-gpu", type=int, default=4)
+    ap.add_argument("--subjects-per-gpu", type=int, default=8, help="independent registrations per GPU (BASELINE C4: 8 per GPU)")
     ap.add_argument("--data-level", type=int, default=7)
     ap.add_argument("--cp-level", type=int, default=5)
     ap.add_argument("--channels", type=int, default=1)
     ap.add_argument("--cpu-rows", type=int, default=1024, help="control points in the bounded CPU sample")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads driving the subjects of one GPU in the e2e leg")
+    ap.add_argument("--e2e-threads", type=int, default=0,
+                    help="host threads driving the subjects of one GPU in the e2e leg (0 = one per subject, at most host cores / ranks)")
     ap.add_argument("--mode", default="subjects", choices=["subjects", "cp", "group"],
                     help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
                          "and triplets sharded over the GPUs (strong scaling); group: groupwise registration "
@@ -675,7 +676,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return evals_per_subject * B * world / float(t.item())
 
-    e2e_threads = max(1, min(B, args.e2e_threads))
+    e2e_threads = args.e2e_threads if args.e2e_threads > 0 else max(1, (os.cpu_count() or 1) // world)
+    e2e_threads = max(1, min(B, e2e_threads))
     e2e_serial = time_e2e(1)
     e2e_value = time_e2e(e2e_threads) if e2e_threads > 1 else e2e_serial
     Vs = len(txyz)
