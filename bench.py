@@ -51,6 +51,27 @@ def measured_peak():
     return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+# ---------------------------------------------------------------------------------------------- the one stdout line
+_RESULT_FD = None
+
+
+def capture_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner, for one) are sent to
+    stderr for the whole run, the result line goes to the original descriptor."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(text):
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        print(text, flush=True)
+    else:
+        os.write(_RESULT_FD, (text + "\n").encode())
+
+
 # ---------------------------------------------------------------------------------------------- synthetic data
 def random_field(xyz, seed, nwaves=32, kmax=6.0):
     rng = np.random.default_rng(seed)
@@ -357,7 +378,7 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
     evals = N * L + L * T * 8
     checksum = float(U.double().sum().item()), float(M.double().sum().item())
     if rank == 0:
-        print(json.dumps({
+        emit_line(json.dumps({
             "metric": metric, "value": evals / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (unary) / f64 (triplet)", "data": "synthetic",
@@ -459,7 +480,7 @@ def bench_group(args, rank, world, local, metric, unit):
     ms_per_step = float(t.item()) / args.steps
     evals = L * S * T * 8
     if rank == 0:
-        print(json.dumps({
+        emit_line(json.dumps({
             "metric": metric, "value": evals / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"groupwise (BASELINE.json configs[4]): {S} subjects, ico{lvl} control grids ({N} points, {T} triangles each), "
@@ -497,6 +518,7 @@ def main():
                          "(falls back to p2p); p2p = one peer store per rank through symmetric-memory mappings; "
                          "nccl = all_gather_into_tensor + re-layout (cp mode only)")
     args = ap.parse_args()
+    capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -524,7 +546,7 @@ def main():
                                  "value_tables_only": r["evals_per_s_resident"], "t_patches_s": r["t_patches"], "t_unary_s": r["t_unary"],
                                  "t_triplet_s": r["t_triplet"]},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit_line(json.dumps(line))
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -722,7 +744,7 @@ def main():
                                         "value_tables_only": r["evals_per_s_resident"]}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        emit_line(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
