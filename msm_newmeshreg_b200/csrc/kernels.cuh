@@ -75,6 +75,8 @@ struct PatchArgs {
     const int* acc_off; const int* acc_idx;                  // accepted uncertain pairs per shard row (fill pass)
     const int* off;                                          // [Ns+1] CSR offsets (fill pass)
     int* idx;                                                // [total]
+    int* slab; int slab_cap;                                 // optional [Ns][slab_cap]: the count pass stashes the definite
+                                                             // members it finds, so the fill pass need not search again
 };
 
 __device__ __forceinline__ void patch_thresholds(double thr, double& c2lo, double& c2hi, float& c2f) {
@@ -193,6 +195,28 @@ __global__ void __launch_bounds__(256) k_bin_fill(BinGrid g, int V, const int* _
     g.sorted[g.cell_start[c] + atomicAdd(g.cell_fill + c, 1)] = i;
 }
 
+// 128 threads: bitonic sort of s_list[0..n) (padded with INT_MAX to the next power of two), then store ascending.
+// Callers synchronise before the call.
+__device__ __forceinline__ void patch_sort_store(int* s_list, int n, int* __restrict__ out, int tid) {
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = n + tid; i < m; i += 128) s_list[i] = 0x7fffffff;
+    __syncthreads();
+    for (int sz = 2; sz <= m; sz <<= 1)
+        for (int st = sz >> 1; st > 0; st >>= 1) {
+            for (int i = tid; i < m; i += 128) {
+                const int j = i ^ st;
+                if (j > i) {
+                    const int vi = s_list[i], vj = s_list[j];
+                    const bool up = (i & sz) == 0;
+                    if ((vi > vj) == up) { s_list[i] = vj; s_list[j] = vi; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = tid; i < n; i += 128) out[i] = s_list[i];
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_patch_binned(PatchArgs a, BinGrid g, int cap /*smem ints, FILL only*/) {
     extern __shared__ int s_list[];
@@ -231,39 +255,41 @@ __global__ void __launch_bounds__(128) k_patch_binned(PatchArgs a, BinGrid g, in
                     }
                 }
                 if (in) {
-                    if (!FILL) mine++;
-                    else { const int p = atomicAdd(&s_n, 1); if (p < cap) s_list[p] = i; }
+                    if (!FILL) {
+                        if (a.slab) { const int p = atomicAdd(&s_n, 1); if (p < a.slab_cap) a.slab[(size_t)row * a.slab_cap + p] = i; }
+                        else mine++;
+                    } else { const int p = atomicAdd(&s_n, 1); if (p < cap) s_list[p] = i; }
                 }
             }
         }
     if (!FILL) {
-        mine = (int)warp_sum((float)mine);
-        if ((tid & 31) == 0) atomicAdd(&s_n, mine);
+        if (!a.slab) {
+            mine = (int)warp_sum((float)mine);
+            if ((tid & 31) == 0) atomicAdd(&s_n, mine);
+        }
         __syncthreads();
-        if (tid == 0) a.counts[row] = s_n;
+        if (tid == 0) a.counts[row] = s_n;   // the true count, also when it exceeds slab_cap (the host then re-searches)
     } else {
         __syncthreads();
         const int n = min(s_n, cap);
-        // bitonic sort of s_list[0..n) padded with INT_MAX to the next power of two
-        int m = 1;
-        while (m < n) m <<= 1;
-        for (int i = n + tid; i < m; i += 128) s_list[i] = 0x7fffffff;
-        __syncthreads();
-        for (int sz = 2; sz <= m; sz <<= 1)
-            for (int st = sz >> 1; st > 0; st >>= 1) {
-                for (int i = tid; i < m; i += 128) {
-                    const int j = i ^ st;
-                    if (j > i) {
-                        const int vi = s_list[i], vj = s_list[j];
-                        const bool up = (i & sz) == 0;
-                        if ((vi > vj) == up) { s_list[i] = vj; s_list[j] = vi; }
-                    }
-                }
-                __syncthreads();
-            }
-        const int o = a.off[row];
-        for (int i = tid; i < n; i += 128) a.idx[o + i] = s_list[i];
+        patch_sort_store(s_list, n, a.idx + a.off[row], tid);
     }
+}
+
+// Fill pass when the count pass stashed its members (PatchArgs::slab): no second search — the definite members come from
+// the slab, the accepted boundary ties from the host's list; sort, store.
+__global__ void __launch_bounds__(128) k_patch_from_slab(PatchArgs a, int cap /*smem ints*/) {
+    extern __shared__ int s_list[];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const int n0 = min(a.counts[row], min(a.slab_cap, cap));
+    int acc0 = 0, acc1 = 0;
+    if (a.acc_off) { acc0 = a.acc_off[row]; acc1 = a.acc_off[row + 1]; }
+    const int n = min(n0 + (acc1 - acc0), cap);
+    const int* __restrict__ sl = a.slab + (size_t)row * a.slab_cap;
+    for (int i = tid; i < n0; i += 128) s_list[i] = sl[i];
+    for (int i = n0 + tid; i < n; i += 128) s_list[i] = a.acc_idx[acc0 + (i - n0)];
+    __syncthreads();
+    patch_sort_store(s_list, n, a.idx + a.off[row], tid);
 }
 
 // exclusive scan of (counts + accepted) over the shard rows; also total and max.  Single CTA.

@@ -114,6 +114,8 @@ struct msm_ctx {
     DevBuf d_counts, d_off, d_idx, d_unc, d_unc_count, d_acc_off, d_acc_idx, d_totmax;
     DevBuf d_px, d_py, d_pz, d_pa, d_pw;
     DevBuf d_scan_sums;       // chunk sums of the voxel-grid scan
+    DevBuf d_slab;            // [Ns][slab_cap] members stashed by the count pass (one-pass patch construction)
+    int slab_cap = 0;         // capacity per control point for the NEXT build (from the last build's largest patch); 0 = off
     DevBuf d_vkey;            // [Vs] spatial sort key of every source vertex (k_vertex_key)
     bool vkey_valid = false;
     DevBuf d_cell_counts, d_cell_start, d_cell_fill, d_cell_of, d_sorted;  // voxel grid of the source vertices
@@ -633,6 +635,7 @@ int msm_build_patches(msm_ctx* ctx) {
     a.counts = ctx->d_counts.as<int>();
     a.unc = ctx->d_unc.as<int2>(); a.unc_cap = unc_cap; a.unc_count = ctx->d_unc_count.as<int>();
     a.acc_off = nullptr; a.acc_idx = nullptr; a.off = nullptr; a.idx = nullptr;
+    a.slab = nullptr; a.slab_cap = 0;
     Timer tm(ctx, "patches");
     // voxel grid over the source vertices (cell >= largest patch chord); brute force only for degenerate sizes
     BinGrid bg{};
@@ -671,6 +674,15 @@ int msm_build_patches(msm_ctx* ctx) {
                 binned = true;
             }
         }
+    }
+    // Patches change little between outer iterations: from the second build on, the count pass stashes the members it finds
+    // in a slab sized from the previous build's largest patch, and the fill pass only sorts them (no second search).  A
+    // patch that outgrew the slab sends the whole build through the two-pass path again.
+    const char* twopass = getenv("MSM_PATCH_TWOPASS");
+    const bool use_slab = binned && ctx->slab_cap > 0 && !(twopass && atoi(twopass));
+    if (use_slab) {
+        CK(ctx->d_slab.ensure((size_t)Ns * ctx->slab_cap * 4));
+        a.slab = ctx->d_slab.as<int>(); a.slab_cap = ctx->slab_cap;
     }
     if (binned) k_patch_binned<false><<<Ns, 128, 0, ctx->stream>>>(a, bg, 0);
     else k_patch<false><<<Ns, 256, 0, ctx->stream>>>(a);
@@ -726,10 +738,18 @@ int msm_build_patches(msm_ctx* ctx) {
     int cap = 1;
     while (cap < ctx->maxP) cap <<= 1;
     if (binned && cap <= 16384) {
-        if (cap * 4 > 48 * 1024) CK(cudaFuncSetAttribute(k_patch_binned<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 4));
-        k_patch_binned<true><<<Ns, 128, (size_t)cap * 4, ctx->stream>>>(a, bg, cap);
+        if (use_slab && ctx->maxP <= ctx->slab_cap) {
+            if (cap * 4 > 48 * 1024) CK(cudaFuncSetAttribute(k_patch_from_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 4));
+            k_patch_from_slab<<<Ns, 128, (size_t)cap * 4, ctx->stream>>>(a, cap);
+        } else {
+            if (cap * 4 > 48 * 1024) CK(cudaFuncSetAttribute(k_patch_binned<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 4));
+            k_patch_binned<true><<<Ns, 128, (size_t)cap * 4, ctx->stream>>>(a, bg, cap);
+        }
+        const long long want = (long long)ctx->maxP + ctx->maxP / 4 + 16;
+        ctx->slab_cap = ((size_t)Ns * (size_t)want * 4 <= ((size_t)512 << 20)) ? (int)want : 0;
     } else {
         k_patch<true><<<Ns, 256, 0, ctx->stream>>>(a);
+        ctx->slab_cap = 0;
     }
     KLAUNCH_CHECK();
     // packed sample streams

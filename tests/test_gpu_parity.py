@@ -62,6 +62,46 @@ def test_patch_range_parameter_and_empty_patches(built):
         ctx.close()
 
 
+def _set_range(ctx, P, r):
+    pr = dict(pb.DEFAULT_PARAMS); pr.update(rng=pb.f32(r))
+    ctx.set_params(meanangle=pyorc.mesh_meanangle(P.cxyz0, P.ctris), mvdmax=P.mvdmax, **pr)
+
+
+@pytest.mark.parametrize("warp", [0.3, 0.0])
+def test_patch_rebuild_paths_give_identical_lists(built, warp):
+    """From the second build on the count pass stashes its members and the fill pass only sorts them; a patch that outgrew
+    that slab sends the build through the two-pass search again.  Every path gives the lists of a fresh context (which the
+    tests above hold to the oracle), boundary ties of the undeformed icosphere (warp=0) included."""
+    P = pb.make_problem(5, 3, 1, seed=9, warp=warp, deform_cp=0.0 if warp == 0.0 else 0.1)
+    Q = pb.make_problem(5, 3, 1, seed=10, warp=0.3, deform_cp=0.1)
+
+    def fresh(sxyz, cxyz, r):
+        c = pb.gpu_context(P, params=dict(rng=pb.f32(r)))
+        c.reset_source(sxyz); c.reset_cpgrid(cxyz); c.build_patches()
+        out = c.patches() + (c.unary_table(),)
+        c.close()
+        return out
+
+    def same(ctx, ref):
+        off, idx = ctx.patches()
+        assert np.array_equal(off, ref[0]) and np.array_equal(idx, ref[1])
+        assert np.array_equal(ctx.unary_table(), ref[2])
+
+    ctx = pb.gpu_context(P, params=dict(rng=pb.f32(0.7)))
+    ref_small = fresh(P.sxyz, P.cxyz, 0.7)
+    ctx.build_patches(); same(ctx, ref_small)                 # first build: two passes
+    ctx.build_patches(); same(ctx, ref_small)                 # second build: from the slab
+    ctx.reset_source(Q.sxyz); ctx.reset_cpgrid(Q.cxyz)        # other geometry, still the slab
+    ctx.build_patches(); same(ctx, fresh(Q.sxyz, Q.cxyz, 0.7))
+    _set_range(ctx, P, 1.5)                                   # patches 4-5x larger than the slab: falls back
+    ctx.build_patches(); same(ctx, fresh(Q.sxyz, Q.cxyz, 1.5))
+    ctx.reset_source(P.sxyz); ctx.reset_cpgrid(P.cxyz)        # and the slab again, sized from the large patches
+    ctx.build_patches(); same(ctx, fresh(P.sxyz, P.cxyz, 1.5))
+    _set_range(ctx, P, 0.01)                                  # (nearly) empty patches through the slab
+    ctx.build_patches(); same(ctx, fresh(P.sxyz, P.cxyz, 0.01))
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ unary
 @pytest.mark.parametrize("kw", [
     dict(data_level=4, cp_level=2, C=1, warp=0.3),
