@@ -130,3 +130,25 @@ def test_assemble_label_major_numpy():
     full = np.arange(19 * 10).reshape(19, 10)
     slices = [full[:, slice(*sh.shard_range(10, r, 4))] for r in range(4)]
     assert np.array_equal(sh.assemble_label_major(slices, 10), full)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE JSON line (library banners go to stderr); the reference arm's line has the
+    keys the driver reads.  Tiny sample so it runs in seconds."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--data-level", "5", "--cp-level", "3", "--cpu-rows", "32"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["higher_is_better"] is True
+    for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"] > 0
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+    assert "workload" in d["config"]
