@@ -89,6 +89,34 @@ def test_triplet_costs(rmode, k_exp):
     m.close()
 
 
+@pytest.mark.parametrize("kw", [
+    dict(simmeasure=1), dict(simmeasure=3),                                  # sign convention (:444-447)
+    dict(rng=pb.f32(0.6)), dict(rng=pb.f32(1.4)),                            # within_controlpt_range (:104-109)
+    dict(rexp=pb.f32(1.0)), dict(lam=pb.f32(0.0)), dict(mu=pb.f32(0.1), kappa=pb.f32(10.0)),
+    dict(rmode=2, dweight=True), dict(rmode=2, anorm=True), dict(rmode=2, dweight=True, anorm=True, rexp=pb.f32(1.0)),
+], ids=lambda kw: ",".join(f"{k}={float(v):g}" for k, v in kw.items()))
+def test_parameter_sweep(kw):
+    """The remaining entries of set_parameters (src/DiscreteCostFunction.cpp:121-136), one at a time, on the unary table,
+    the patch lists and a sample of triplet costs."""
+    P = pb.make_problem(3, 2, 1, seed=61, warp=0.25, deform_cp=0.12)
+    m = ref_model(P, **kw)
+    m.reset_cpgrid(P.cxyz)
+    m.setup()
+    cf = pb.oracle_costfunction(P, params=kw); cf.get_source_data()
+    po, pr = cf.patches(), pyrefcost.patches(m)
+    assert all(np.array_equal(a, b) for a, b in zip(po, pr))
+    good = np.ones(P.N, bool); good[pb.singular_nodes(P)] = False
+    assert np.abs(m.unary() - cf.unary_costs())[:, good].max() < 1e-12
+    rng = np.random.default_rng(7)
+    q = np.stack([rng.integers(0, P.T, 3000)] + [rng.integers(0, P.L, 3000) for _ in range(3)], 1).astype(np.int32)
+    r, o = m.costs("triplet", q), cf.triplet_costs(q)
+    sing = np.isin(P.triplets[q[:, 0]], pb.singular_nodes(P)).any(1)
+    assert pb.rel_err(r[~sing], o[~sing], 1e-9).max() < 1e-9
+    if float(kw.get("lam", 1.0)) == 0.0:
+        assert not r.any()
+    m.close()
+
+
 def test_pairwise_costs_and_total():
     """computePairwiseCost (:256-296), evaluateTotalCostSum (:35-70)."""
     P = pb.make_problem(3, 2, 1, seed=52, warp=0.2, deform_cp=0.1)
