@@ -152,3 +152,92 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"] > 0
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
     assert "workload" in d["config"]
+
+
+# ------------------------------------------------------------------------------------------------ hierarchy builder (CPU)
+@pytest.fixture(scope="module")
+def ich():
+    """tests/cpu_hierarchy.cpp: the product's host-side hierarchy builder (csrc/ico_hierarchy.h) behind a small C ABI."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out_dir = os.path.join(here, "_build"); os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcpu_hierarchy.so")
+    src = os.path.join(here, "cpu_hierarchy.cpp")
+    hdr = os.path.join(here, "..", "msm_newmeshreg_b200", "csrc", "ico_hierarchy.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", so])
+    L = ctypes.CDLL(so)
+    L.ich_error.restype = ctypes.c_char_p
+    return L
+
+
+def _ich_build(L, xyz, tris):
+    xyz = np.ascontiguousarray(xyz, np.float64); tris = np.ascontiguousarray(tris, np.int32)
+    return L.ich_build(xyz.ctypes.data_as(ctypes.c_void_p), len(xyz), tris.ctypes.data_as(ctypes.c_void_p), len(tris))
+
+
+def _sphere_points(n, seed):
+    p = np.random.default_rng(seed).normal(size=(n, 3))
+    return 100.0 * p / np.linalg.norm(p, axis=1, keepdims=True)
+
+
+@pytest.mark.parametrize("level", [0, 1, 3, 5])
+def test_hierarchy_descent_equals_brute_force_closest_triangle(ich, level):
+    """Base face + `level` scalar four-way steps over the tables ico_hierarchy.h builds find the triangle the oracle's
+    brute-force search finds, with its barycentric weights — for any vertex / face numbering and orientation."""
+    from oracle import pyorc
+    xyz, tris = pyorc.icosphere(level)
+    rng = np.random.default_rng(level)
+    th = 0.9
+    R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]]) @ \
+        np.array([[np.cos(0.3), -np.sin(0.3), 0], [np.sin(0.3), np.cos(0.3), 0], [0, 0, 1]])
+    vp = rng.permutation(len(xyz)); inv = np.argsort(vp)
+    xyz2 = (xyz @ R.T)[vp]
+    tris2 = inv[tris][rng.permutation(len(tris))]
+    tris2 = np.stack([np.roll(t, rng.integers(0, 3)) for t in tris2]).astype(np.int32)
+    assert _ich_build(ich, xyz2, tris2) == 0, ich.ich_error()
+    assert ich.ich_depth() == level
+    pts = _sphere_points(20000, 100 + level)
+    tri = np.empty(len(pts), np.int32); w = np.empty((len(pts), 3))
+    ich.ich_locate(pts.ctypes.data_as(ctypes.c_void_p), len(pts), tri.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p))
+    bt, bw = pyorc.locate(xyz2, tris2, pts, brute=True)
+    inside = w.min(1) > 1e-9                                  # a point on an edge belongs to either triangle
+    assert inside.mean() > 0.99
+    assert np.array_equal(tri[inside], bt[inside])
+    assert np.abs(w - bw)[inside].max() < 1e-12
+    assert np.abs(w.sum(1) - 1).max() < 1e-14 and w.min() >= 0
+
+
+@pytest.mark.parametrize("h", [0, 1, 2, 3])
+def test_hint_frame_walk_reaches_the_same_triangle(ich, h):
+    """k_unary's route: coordinates in the frame of the level-h face under ANOTHER point (the control point), edge walk
+    with the hT tables, descent of the remaining levels — same triangle and weights as the direct descent."""
+    from oracle import pyorc
+    level = 4
+    xyz, tris = pyorc.icosphere(level)
+    assert _ich_build(ich, xyz, tris) == 0, ich.ich_error()
+    pts = _sphere_points(20000, 7)
+    rng = np.random.default_rng(8)
+    edge_h = 100.0 * 1.1071487177940904 / 2 ** h             # arc length of a level-h edge
+    d = rng.normal(size=pts.shape) * (0.8 * edge_h / np.sqrt(3))
+    starts = pts + d; starts *= 100.0 / np.linalg.norm(starts, axis=1, keepdims=True)
+    tri = np.empty(len(pts), np.int32); w = np.empty((len(pts), 3))
+    tri2 = np.empty(len(pts), np.int32); w2 = np.empty((len(pts), 3)); steps = np.empty(len(pts), np.int32)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ich.ich_locate(P(pts), len(pts), P(tri), P(w))
+    assert ich.ich_locate_via_hint(h, P(starts), P(pts), len(pts), P(tri2), P(w2), P(steps)) == 0, ich.ich_error()
+    inside = (w.min(1) > 1e-9) & (w2.min(1) > 1e-9)
+    assert inside.mean() > 0.99
+    assert np.array_equal(tri[inside], tri2[inside])
+    assert np.abs(w - w2)[inside].max() < 1e-11
+    assert steps.max() < 16 and steps.max() > 0               # some points did cross edges
+
+
+def test_hierarchy_builder_rejects_what_is_not_a_regular_icosphere(ich):
+    from oracle import pyorc
+    xyz, tris = pyorc.icosphere(3)
+    assert _ich_build(ich, pb.smooth_warp(xyz, 1, 2.0), tris) != 0 and re.search(b"icos|sphere", ich.ich_error())
+    assert _ich_build(ich, xyz[:-1], tris[:-2]) != 0
+    bad = tris.copy(); bad[5] = bad[6]                         # a face twice, another missing
+    assert _ich_build(ich, xyz, bad) != 0
+    assert _ich_build(ich, xyz * np.array([1.0, 1.0, 1.02]), tris) != 0 and re.search(b"sphere", ich.ich_error())
