@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -22,6 +23,14 @@ using namespace msm;
 
 namespace {
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device), not per context: contexts driven from different
+// threads hold this lock from setting it to launching, so that a smaller request of another context cannot slip in between.
+// Only launches that need more than the default 48 KB take it.
+std::mutex g_big_smem_mtx;
+struct BigSmemLock {
+    std::unique_lock<std::mutex> lk;
+    explicit BigSmemLock(size_t smem) : lk(g_big_smem_mtx, std::defer_lock) { if (smem > 48 * 1024) lk.lock(); }
+};
 thread_local std::string g_create_error;   // per thread: contexts may be created concurrently
 
 struct DevBuf {
@@ -738,6 +747,7 @@ int msm_build_patches(msm_ctx* ctx) {
     int cap = 1;
     while (cap < ctx->maxP) cap <<= 1;
     if (binned && cap <= 16384) {
+        BigSmemLock big((size_t)cap * 4);
         if (use_slab && ctx->maxP <= ctx->slab_cap) {
             if (cap * 4 > 48 * 1024) CK(cudaFuncSetAttribute(k_patch_from_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 4));
             k_patch_from_slab<<<Ns, 128, (size_t)cap * 4, ctx->stream>>>(a, cap);
@@ -899,6 +909,7 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
         k_unary<Q><<<grid, 256, smem, ctx->stream>>>(a);                                                            \
     } while (0)
     {
+        BigSmemLock big(smem);
         Timer tmain(ctx, "unary_main");
         switch (CQ) {
             case 0: LAUNCH_UNARY(0); break;
@@ -967,6 +978,7 @@ int msm_triplet_table_dev(msm_ctx* ctx, int t0, int t1, float* d_out) {
     const int L = ctx->L;
     const size_t smem = (size_t)9 * L * sizeof(double) + (size_t)L * L * L * sizeof(float);
     if (smem > 200 * 1024) FAIL("msm_triplet_table: label set too large for the full table kernel");
+    BigSmemLock big(smem);
     if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_triplet_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Timer tm(ctx, "triplet_table");
     k_triplet_table<<<t1 - t0, 256, smem, ctx->stream>>>(trip_args(ctx), t0, d_out);
