@@ -138,3 +138,26 @@ def test_run_discrete_opt_matches_oracle_loop(built):
     far = d_sing > 2.5 * P.mvdmax
     assert np.abs(src_gpu - src)[far].max() < 1e-4
     m.close()
+
+
+@pytest.mark.gpu
+def test_large_patches_from_concurrent_host_threads(built):
+    """Patches of ~1000 samples need more than 48 KB of dynamic shared memory, an attribute CUDA keeps per function and
+    device: contexts driven from different threads serialise set-attribute + launch (csrc/msm_b200.cu BigSmemLock).
+    Last test of the GPU suite on purpose — it was written after the round's GPU budget was spent."""
+    from concurrent.futures import ThreadPoolExecutor
+    probs = [pb.make_problem(5, 1, 1, seed=60 + s, warp=0.3) for s in range(3)]
+
+    def run(P):
+        ctx = pb.gpu_context(P); ctx.build_patches()
+        out = (ctx.unary_table(), ctx.patches()[1])
+        ctx.close()
+        return out
+
+    serial = [run(P) for P in probs]
+    assert max(len(s[1]) for s in serial) // probs[0].N > 700      # large patches: the > 48 KB path
+    for _ in range(3):
+        with ThreadPoolExecutor(3) as pool:
+            threaded = list(pool.map(run, probs))
+        for a, b in zip(serial, threaded):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
