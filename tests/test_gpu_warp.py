@@ -146,7 +146,8 @@ def test_large_patches_from_concurrent_host_threads(built):
     device: contexts driven from different threads serialise set-attribute + launch (csrc/msm_b200.cu BigSmemLock).
     Last test of the GPU suite on purpose — it was written after the round's GPU budget was spent."""
     from concurrent.futures import ThreadPoolExecutor
-    probs = [pb.make_problem(5, 1, 1, seed=60 + s, warp=0.3) for s in range(3)]
+    # ico6 data / ico2 control grid (configs[0]): 162 control points x 5 label groups of 4 labels, ~57 KB per CTA
+    probs = [pb.make_problem(6, 2, 1, seed=60 + s, warp=0.3) for s in range(3)]
 
     def run(P):
         ctx = pb.gpu_context(P); ctx.build_patches()
