@@ -599,7 +599,7 @@ __device__ __forceinline__ double trip_cost_fast(const DevParams& p, const TripG
     return weight * p.lambda * (cost * cost);
 }
 __host__ __device__ inline bool trip_fast_ok(const DevParams& p) {
-    return p.rexp == 2.0 && (p.group || (p.rmode == 3 && p.k_exp == 2.0));
+    return p.rexp == 2.0 && (p.group || (p.rmode == 3 && p.k_exp == 2.0)) && p.lambda >= 0.0 && p.mu >= 0.0 && p.kappa >= 0.0;
 }
 
 template <typename OutT, bool FAST>

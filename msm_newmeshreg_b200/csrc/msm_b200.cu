@@ -18,6 +18,7 @@
 #include "ico_hierarchy.h"
 #include "kernels.cuh"
 #include "meshwarp.cuh"
+#include "triplet.cuh"
 
 using namespace msm;
 
@@ -134,7 +135,7 @@ struct msm_ctx {
     DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
 
     // outputs / scratch
-    DevBuf d_unary, d_scratch, d_scratch2;
+    DevBuf d_unary, d_scratch, d_scratch2, d_tprep;
     PinBuf h_pin;
     std::vector<float> h_unary;   // last unary table, shard rows [L][Ns], for msm_total_cost
     int h_unary_k0 = 0, h_unary_ns = 0;
@@ -405,6 +406,8 @@ int msm_synchronize(msm_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStrea
 
 int msm_set_params(msm_ctx* ctx, const msm_params* p) {
     if (p->bary_orthogonal) FAIL("bary_orthogonal: only the radial projection (A4 default) is implemented on the device");
+    if (p->range != ctx->par.range) { ctx->have_patches = false; ctx->have_unary = false; }   // patches were built for the old range
+    if (p->simmeasure != ctx->par.simmeasure) ctx->have_unary = false;                        // sign of the cached table
     ctx->par = *p;
     return 0;
 }
@@ -976,6 +979,29 @@ int msm_triplet_table_dev(msm_ctx* ctx, int t0, int t1, float* d_out) {
     if (t0 < 0 || t1 > ctx->Tn || t0 > t1) FAIL("msm_triplet_table: bad triplet range");
     if (t0 == t1) return 0;
     const int L = ctx->L;
+    const DevParams dp = dev_params(ctx);
+    if (trip_fast_ok(dp) && triplet_table_smem(L) <= 200 * 1024) {
+        const size_t smem = triplet_table_smem(L);
+        const int nt = t1 - t0;
+        BigSmemLock big(smem);
+        CK(ctx->d_tprep.ensure((size_t)nt * triplet_rec_bytes(L)));
+        unsigned char* recs = ctx->d_tprep.as<unsigned char>();
+        Timer tm(ctx, "triplet_table");
+        k_triplet_prep<<<(nt + 3) / 4, 128, 0, ctx->stream>>>(trip_args(ctx), t0, nt, recs);
+        KLAUNCH_CHECK();
+        if (L == 19) {   // the standard label sets: compile-time label count; one CTA per triplet, 6 per SM
+            const size_t sm1 = triplet_table_smem(L, 1);
+            k_triplet_table_fast<19, 6><<<nt, kTabThreads, sm1, ctx->stream>>>(trip_args(ctx), strain_consts(dp), recs, nt, 1, d_out);
+        } else {
+            int nsm = 148;
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+            const int per_sm = std::max(1, std::min(5, (int)((200 * 1024) / smem)));
+            if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_triplet_table_fast<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_triplet_table_fast<0, 1><<<std::min(nt, nsm * per_sm), kTabThreads, smem, ctx->stream>>>(trip_args(ctx), strain_consts(dp), recs, nt, 2, d_out);
+        }
+        KLAUNCH_CHECK();
+        return 0;
+    }
     const size_t smem = (size_t)9 * L * sizeof(double) + (size_t)L * L * L * sizeof(float);
     if (smem > 200 * 1024) FAIL("msm_triplet_table: label set too large for the full table kernel");
     BigSmemLock big(smem);
@@ -996,11 +1022,24 @@ int msm_triplet_table(msm_ctx* ctx, int t0, int t1, float* out) {
     return 0;
 }
 
-// picks the lean kernel for the default regulariser settings (kernels.cuh trip_cost_fast)
-#define LAUNCH_TRIPLET_MOVES(OUT_T, grid, ...)                                                       \
-    do {                                                                                             \
-        if (trip_fast_ok(dev_params(ctx))) k_triplet_moves<OUT_T, true><<<(grid), 128, 0, ctx->stream>>>(__VA_ARGS__);  \
-        else k_triplet_moves<OUT_T, false><<<(grid), 128, 0, ctx->stream>>>(__VA_ARGS__);             \
+// The default regulariser settings (strain, k = 2, exponent 2; or the group rules) run the shared-edge kernel of
+// triplet.cuh (grid: triplets x labels); every other parameter set the generic one (kernels.cuh trip_cost).
+#ifndef MSM_MOVES_AG
+#define MSM_MOVES_AG 5
+#endif
+constexpr int kMovesAG = MSM_MOVES_AG;   // proposal labels per thread of k_triplet_moves_fast (measured best of 1..19)
+constexpr int kMovesBlock = 64;
+#define LAUNCH_TRIPLET_MOVES(OUT_T, a_, T_, lab_, alpha_, out_, peers_, tfull_)                                             \
+    do {                                                                                                                 \
+        const DevParams dp_ = dev_params(ctx);                                                                           \
+        const int nal_ = (alpha_) < 0 ? ctx->L : 1;                                                                      \
+        if (trip_fast_ok(dp_)) {                                                                                         \
+            const dim3 grid_((unsigned)(((T_) + kMovesBlock - 1) / kMovesBlock), (unsigned)((nal_ + kMovesAG - 1) / kMovesAG)); \
+            k_triplet_moves_fast<OUT_T, kMovesAG><<<grid_, kMovesBlock, 0, ctx->stream>>>(a_, strain_consts(dp_), T_, lab_, alpha_, out_, peers_, tfull_); \
+        } else {                                                                                                         \
+            const long long n_ = (long long)nal_ * (T_);                                                                 \
+            k_triplet_moves<OUT_T, false><<<(unsigned)((n_ + 127) / 128), 128, 0, ctx->stream>>>(a_, T_, lab_, alpha_, out_, peers_, tfull_); \
+        }                                                                                                                \
     } while (0)
 
 int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, int t0, int t1, float* d_out) {
@@ -1009,11 +1048,10 @@ int msm_triplet_moves_range_dev(msm_ctx* ctx, const int* d_labeling, int alpha, 
     if (alpha >= ctx->L) FAIL("msm_triplet_moves: label out of range");
     if (t0 < 0 || t1 > ctx->Tn || t0 > t1) FAIL("msm_triplet_moves: bad triplet range");
     if (t0 == t1) return 0;
-    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * (t1 - t0);
     TripArgs a = trip_args(ctx);
     a.t_off = t0;
     Timer tm(ctx, "triplet_moves");
-    LAUNCH_TRIPLET_MOVES(float, (unsigned)((n + 127) / 128), a, t1 - t0, d_labeling, alpha, d_out);
+    LAUNCH_TRIPLET_MOVES(float, a, t1 - t0, d_labeling, alpha, d_out, PeerSet{}, 0);
     KLAUNCH_CHECK();
     return 0;
 }
@@ -1027,11 +1065,10 @@ int msm_triplet_moves_range_peers(msm_ctx* ctx, const int* d_labeling, int alpha
     PeerSet ps{};
     if (make_peer_set(ctx, peer_tables, world, multicast_table, ps)) return 1;
     if (t0 == t1) return 0;
-    const long long n = (long long)(alpha < 0 ? ctx->L : 1) * (t1 - t0);
     TripArgs a = trip_args(ctx);
     a.t_off = t0;
     Timer tm(ctx, "triplet_moves");
-    LAUNCH_TRIPLET_MOVES(float, (unsigned)((n + 127) / 128), a, t1 - t0, d_labeling, alpha, (float*)nullptr, ps, ctx->Tn);
+    LAUNCH_TRIPLET_MOVES(float, a, t1 - t0, d_labeling, alpha, (float*)nullptr, ps, ctx->Tn);
     KLAUNCH_CHECK();
     return 0;
 }
@@ -1052,7 +1089,7 @@ int msm_triplet_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out)
     CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timer tm(ctx, "triplet_moves");
-        LAUNCH_TRIPLET_MOVES(double, (unsigned)((n / 8 + 127) / 128), trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha, ctx->d_scratch2.as<double>());
+        LAUNCH_TRIPLET_MOVES(double, trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha, ctx->d_scratch2.as<double>(), PeerSet{}, 0);
         KLAUNCH_CHECK();
     }
     CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1073,7 +1110,7 @@ int msm_triplet_moves_f32(msm_ctx* ctx, const int* labeling, int alpha, float* o
     CK(cudaMemcpyAsync(ctx->d_scratch.p, labeling, (size_t)ctx->N * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
         Timer tm(ctx, "triplet_moves");
-        LAUNCH_TRIPLET_MOVES(float, (unsigned)((n / 8 + 127) / 128), trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha, ctx->d_scratch2.as<float>());
+        LAUNCH_TRIPLET_MOVES(float, trip_args(ctx), ctx->Tn, ctx->d_scratch.as<int>(), alpha, ctx->d_scratch2.as<float>(), PeerSet{}, 0);
         KLAUNCH_CHECK();
     }
     CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1277,9 +1314,19 @@ int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]) {
     sums[0] = sums[1] = sums[2] = 0.0;
     for (int i = 0; i < ctx->N; i++)
         if (labeling[i] < 0 || labeling[i] >= ctx->L) FAIL("msm_total_cost: labeling out of range");
-    if (ctx->have_unary)
-        for (int r = 0; r < ctx->h_unary_ns; r++)
-            sums[0] += (double)ctx->h_unary[(size_t)labeling[ctx->h_unary_k0 + r] * ctx->h_unary_ns + r];
+    if (!ctx->par.group) {
+        // unary term: needs the host copy of the whole table that msm_unary_table leaves behind (the device-resident and
+        // sharded variants do not); the group model has no unary term (src/DiscreteCostFunction.h:34)
+        if (ctx->Vs > 0 && ctx->have_target && ctx->Ct > 0) {
+            if (!ctx->have_unary)
+                FAIL("msm_total_cost: no unary table — call msm_unary_table first (msm_unary_table_dev / _peers keep no host copy, and "
+                     "set_cpgrid / set_labels / set_shard / build_patches invalidate it)");
+            if (ctx->h_unary_k0 != 0 || ctx->h_unary_ns != ctx->N)
+                FAIL("msm_total_cost: the unary table covers only this context's shard; sum the shards' energies on the caller's side");
+            for (int r = 0; r < ctx->h_unary_ns; r++)
+                sums[0] += (double)ctx->h_unary[(size_t)labeling[ctx->h_unary_k0 + r] * ctx->h_unary_ns + r];
+        }
+    }
     if (ctx->P > 0 && !ctx->par.group) {
         if (check_pairs(ctx)) return 1;
         std::vector<int> q((size_t)ctx->P * 3);
@@ -1294,6 +1341,16 @@ int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]) {
         std::vector<double> r(ctx->P);
         CK(cudaMemcpyAsync(r.data(), ctx->d_scratch2.p, (size_t)ctx->P * 8, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        for (double v : r) sums[1] += v;
+    }
+    if (ctx->P > 0 && ctx->par.group) {
+        // group data term (src/DiscreteGroupCostFunction.cpp:32-54) over the labelling
+        if (ctx->n_maps != (long long)ctx->N * ctx->L) FAIL("msm_total_cost: group model with pairs but no patch data (msm_set_group_patches)");
+        std::vector<int> q((size_t)ctx->P * 3), hp((size_t)ctx->P * 2);
+        CK(cudaMemcpy(hp.data(), ctx->d_pairs.p, hp.size() * 4, cudaMemcpyDeviceToHost));
+        for (int p = 0; p < ctx->P; p++) { q[3 * p] = p; q[3 * p + 1] = labeling[hp[2 * p]]; q[3 * p + 2] = labeling[hp[2 * p + 1]]; }
+        std::vector<double> r(ctx->P);
+        if (msm_group_pair_costs(ctx, ctx->P, q.data(), r.data())) return 1;
         for (double v : r) sums[1] += v;
     }
     if (ctx->Tn > 0) {

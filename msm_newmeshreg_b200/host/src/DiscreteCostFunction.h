@@ -128,6 +128,7 @@ public:
         it = ALLPARAMS.find("numthreads"); _threads = boost::get<int>(it->second);
         it = ALLPARAMS.find("dOPT"); dopt = boost::get<std::string>(it->second);
         params_dirty = true;
+        tables_epoch++;   // every cached table was produced with the old parameters
     }
 
     //---COST CALCULATION---//
@@ -197,7 +198,7 @@ public:
         labels_dirty = true;
     }
     virtual void set_patch_data(const std::vector<std::map<int, double>>& patches) {}
-    virtual void set_spacings(const NEWMAT::ColumnVector& spacings, double MAX) { MAXSEP = spacings; MVDmax = MAX; grid_dirty = params_dirty = true; }
+    virtual void set_spacings(const NEWMAT::ColumnVector& spacings, double MAX) { MAXSEP = spacings; MVDmax = MAX; grid_dirty = params_dirty = true; tables_epoch++; }
     void set_octrees(std::shared_ptr<newresampler::Octree>&) {}  // the device-side hierarchy is built in set_target
     virtual void reset_source(const newresampler::Mesh& source, int num = 0) { _SOURCE = source; source_xyz_dirty = true; }
     virtual void reset_CPgrid(const newresampler::Mesh& grid, int num = 0) { _CPgrid = grid; cp_xyz_dirty = true; }
@@ -209,6 +210,13 @@ public:
     }
     void initialize_regulariser() {}  // anatomical modes only
     void reset_anatomical() {}
+    // src/DiscreteCostFunction.h:146-163 — anatomical regulariser modes 4/5: outside the accelerated path
+    void set_anatomical(const newresampler::Mesh&, const newresampler::Mesh&, const newresampler::Mesh&, const newresampler::Mesh&) {
+        throw MeshregException("set_anatomical: the anatomical regulariser modes (regoption 4/5) are not part of the GPU cost-evaluation path");
+    }
+    void set_anatomical_neighbourhood(const std::vector<std::map<int, double>>&, const std::vector<std::vector<int>>&) {
+        throw MeshregException("set_anatomical_neighbourhood: the anatomical regulariser modes (regoption 4/5) are not part of the GPU cost-evaluation path");
+    }
     // AbsoluteWeights (resample_weights, :364-383): identically 1 for unit weights; otherwise supplied by the caller
     // because the reference obtains them from FSL's metric_resample ([EXT] A8).
     void set_absolute_weights(const std::vector<double>& aw) { abs_weights = aw; grid_dirty = true; }

@@ -219,6 +219,16 @@ public:
 
     //---SETUP MODEL---//
     virtual void set_meshspace(const newresampler::Mesh& target, const newresampler::Mesh& source, int num = 1) { m_TARGET = target; m_SOURCE = source; }
+    // src/DiscreteModel.h:99-105 — called by the driver when anatomical meshes are supplied (src/mesh_registration.cpp:77-78,
+    // regulariser modes 4/5).  Those modes are outside the accelerated path: the calls exist so that
+    // the driver compiles unchanged, and say so when they are reached.
+    void set_anatomical_meshspace(const newresampler::Mesh& ref_sphere, const newresampler::Mesh& ref_anat, const newresampler::Mesh& source_sphere,
+                                  const newresampler::Mesh& source_anat) {
+        costfct->set_anatomical(ref_sphere, ref_anat, source_sphere, source_anat);
+    }
+    void set_anatomical_neighbourhood(const std::vector<std::map<int, double>>& weights, const std::vector<std::vector<int>>& neighbourhood) {
+        costfct->set_anatomical_neighbourhood(weights, neighbourhood);
+    }
     void set_featurespace(const std::shared_ptr<featurespace>& FEATURES) { FEAT = FEATURES; costfct->set_featurespace(FEATURES); }
     void setupCostFunctionWeighting(const NEWMAT::Matrix& Weight) { costfct->set_dataaffintyweighting(Weight); }
     virtual void reset_meshspace(const newresampler::Mesh& source, int num = 0) { m_SOURCE = source; costfct->reset_source(source); }

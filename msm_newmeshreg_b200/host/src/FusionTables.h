@@ -28,6 +28,8 @@ public:
         const int* triplets = energy->getTriplets();
         int* labeling = energy->getLabeling();
         const std::vector<double>& U = cf->unaryTable();            // [L][N]
+        if (U.size() != (size_t)L * N)
+            throw MeshregException("FusionTables::optimize: the model has no [L][N] unary table (group models go through FusionTables::optimize_group)");
         std::vector<float> moves((size_t)std::max(T, 1) * 8);       // [T][8] of the current proposal label
         auto binary = std::make_shared<DiscreteModelDummy>();
         const int NUM_SWEEPS = 2;                                   // Fusion.h:124

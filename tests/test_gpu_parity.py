@@ -315,8 +315,16 @@ def test_triplet_table_and_moves(built):
                 q.append([t, alpha if combo & 4 else a, alpha if combo & 2 else b, alpha if combo & 1 else c])
         o = cf.triplet_costs(np.array(q, np.int32)).reshape(P.T, 8)
         _check(mv, o, 1e-3 * pb.DEFAULT_PARAMS["lam"], f"moves alpha={alpha}", tol=1e-9)
+    with pytest.raises(Exception, match="no unary table"):           # the energy is never silently partial
+        ctx.total_cost(lab)
+    ctx.build_patches(); U = ctx.unary_table(); cf.get_source_data()
     s = ctx.total_cost(lab)
     assert abs(s[2] - cf.total(lab, use_unary=False)) <= 1e-9 * abs(s[2])  # evaluateTotalCostSum, triplet part
+    assert abs(s[0] - U[lab, np.arange(P.N)].sum()) <= 1e-6 * abs(s[0])     # unary part = the table at the labelling
+    assert abs(sum(s) - cf.total(lab, use_unary=True)) <= 1e-5 * abs(sum(s))
+    ctx.set_shard(0, P.N // 2); ctx.build_patches(); ctx.unary_table()
+    with pytest.raises(Exception, match="shard"):
+        ctx.total_cost(lab)
     ctx.close()
 
 
@@ -409,6 +417,7 @@ def test_pair_table_parity(built):
         # moves small pairwise costs by ~1e-6 relative.  The device uses atan2(|a x b|, a.b) and returns the identity.
         _check(ctx.pair_table(), cf.pair_table(), 1e-3 * pb.DEFAULT_PARAMS["lam"], f"pair table rexp={rexp}", tol=TOL)
         lab = np.random.default_rng(2).integers(0, P.L, P.N).astype(np.int32)
+        ctx.build_patches(); ctx.unary_table()
         s = ctx.total_cost(lab)
         assert abs(s[1] - cf.total(lab, use_unary=False)) <= TOL * max(abs(s[1]), 1e-12)
         ctx.close()
