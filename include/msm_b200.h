@@ -99,6 +99,9 @@ int msm_set_group(msm_ctx* ctx, int S, int N_subj, int T_subj);
 int msm_build_patches(msm_ctx* ctx);
 /* _sourceinrange as CSR: offsets int[N+1] (only this shard's rows are non-empty), idx int[total]. */
 int msm_patch_count(msm_ctx* ctx, long long* total);
+/* Introspection for tests/bench: how many builds of this context took the one-pass path (second and later builds of a level,
+ * no boundary ties: csrc/patchfast.cuh) and how many the exact two-pass path.  Both give identical patches and tables. */
+int msm_patch_build_stats(const msm_ctx* ctx, long long* one_pass, long long* two_pass);
 int msm_get_patches(msm_ctx* ctx, int* offsets, int* idx);
 
 /* computeUnaryCosts (src/DiscreteCostFunction.cpp:306-313): out double[L][N] (rows of other shards untouched). */

@@ -27,7 +27,7 @@ EXPORTS = [
     "msm_set_target", "msm_set_source", "msm_reset_source", "msm_set_cpgrid", "msm_reset_cpgrid", "msm_set_shard", "msm_set_labels",
     "msm_set_pairs", "msm_set_triplets", "msm_set_group", "msm_build_patches", "msm_patch_count", "msm_get_patches",
     "msm_unary_table", "msm_unary_table_dev", "msm_triplet_costs", "msm_triplet_table", "msm_triplet_table_dev", "msm_triplet_moves",
-    "msm_triplet_moves_f32", "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count",
+    "msm_triplet_moves_f32", "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count", "msm_patch_build_stats",
     "msm_set_timing", "msm_last_kernel_ms", "msm_timing_collect", "msm_set_group_patches", "msm_group_pair_costs",
     "msm_group_pair_moves", "msm_mesh_interpolate",
 ]
@@ -190,6 +190,12 @@ class Context:
         off = np.zeros(self.N + 1, np.int32); idx = np.zeros(max(tot.value, 1), np.int32)
         self._ck(lib().msm_get_patches(self._h, off.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip)))
         return off, idx[:tot.value]
+
+    def patch_build_stats(self):
+        """(one-pass builds, exact two-pass builds) of this context so far."""
+        a, b = C.c_longlong(), C.c_longlong()
+        self._ck(lib().msm_patch_build_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def unary_table(self, out=None):
         if out is None:

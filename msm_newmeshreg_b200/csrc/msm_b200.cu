@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "meshwarp.cuh"
 #include "triplet.cuh"
+#include "patchfast.cuh"
 
 using namespace msm;
 
@@ -131,6 +132,10 @@ struct msm_ctx {
     DevBuf d_cell_counts, d_cell_start, d_cell_fill, d_cell_of, d_sorted;  // voxel grid of the source vertices
     DevBuf d_pcx, d_pcy, d_pcz, d_hint_face, d_lab12, d_tref;  // k_unary_setup outputs
     int pack_cp = 0;
+    bool patches_padded = false;   // packed streams are fixed-capacity rows [Ns][pad_cap] (one-pass build, patchfast.cuh), not CSR
+    int pad_cap = 0;
+    DevBuf d_pflags;
+    long long fast_builds = 0, exact_builds = 0;
 
     DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
 
@@ -687,6 +692,71 @@ int msm_build_patches(msm_ctx* ctx) {
             }
         }
     }
+    // One-pass build (patchfast.cuh): from the second build of a level on, when the previous build's largest patch bounds
+    // this one's.  Falls through to the exact two-pass path below on boundary ties or an overflowing row.
+    {
+        const char* slow = getenv("MSM_PATCH_TWOPASS");
+        const char* nosort = getenv("MSM_PATCH_NOSORT");
+        const int cap = ctx->slab_cap;
+        const int Cp = ctx->multivariate ? 4 * ((ctx->Cs + 3) / 4) : 1;
+        const size_t rows = (size_t)Ns * (size_t)std::max(cap, 1);
+        if (binned && cap > 0 && cap <= 4096 && ctx->have_target && !(slow && atoi(slow)) && !(nosort && atoi(nosort)) &&
+            (ctx->multivariate || ctx->Cs == 1) && rows * 4 * (5 + 2 * (size_t)Cp) <= ((size_t)2 << 30)) {
+            if (!ctx->vkey_valid) {
+                CK(ctx->d_vkey.ensure((size_t)ctx->Vs * 4));
+                k_vertex_key<<<(ctx->Vs + 127) / 128, 128, 0, ctx->stream>>>(ctx->Vs, ctx->d_src.as<double>(), ico_dev(ctx), ctx->d_vkey.as<int>());
+                KLAUNCH_CHECK();
+                ctx->vkey_valid = true;
+            }
+            CK(ctx->d_idx.ensure(rows * 4));
+            CK(ctx->d_px.ensure(rows * 4)); CK(ctx->d_py.ensure(rows * 4)); CK(ctx->d_pz.ensure(rows * 4));
+            CK(ctx->d_pa.ensure(rows * 4 * Cp)); CK(ctx->d_pw.ensure(rows * 4 * Cp));
+            CK(ctx->d_pflags.ensure(16));
+            CK(cudaMemsetAsync(ctx->d_pflags.p, 0, 16, ctx->stream));
+            PatchFastArgs f;
+            f.k_begin = ctx->k_begin; f.Ns = Ns; f.V = ctx->Vs; f.cap = cap; f.g = bg;
+            f.sxf = a.sxf; f.syf = a.syf; f.szf = a.szf; f.src = a.src; f.cp = a.cp; f.maxsep = a.maxsep; f.range = a.range;
+            f.vkey = ctx->d_vkey.as<int>();
+            f.Cp = Cp; f.C = ctx->Cs; f.wrows = ctx->wrows; f.univariate = ctx->multivariate ? 0 : 1;
+            f.feat = ctx->d_sfeat.as<double>(); f.wgt = ctx->d_swgt.as<float>();
+            f.counts = ctx->d_counts.as<int>(); f.idx = ctx->d_idx.as<int>();
+            f.px = ctx->d_px.as<float>(); f.py = ctx->d_py.as<float>(); f.pz = ctx->d_pz.as<float>();
+            f.pa = ctx->d_pa.as<float>(); f.pw = ctx->d_pw.as<float>();
+            f.flags = ctx->d_pflags.as<int>();
+            const size_t smem = (size_t)kPatchWarps * 2 * cap * sizeof(int);
+            {
+                BigSmemLock big(smem);
+                const unsigned grid = (unsigned)((Ns + kPatchWarps - 1) / kPatchWarps);
+                const char* er = getenv("MSM_PATCH_R");
+                const int R = er ? atoi(er) : std::min(4, (cap + 31) / 32);
+#define PATCH_FUSED(RR)                                                                                                        \
+    do {                                                                                                                       \
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_patch_fused<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_patch_fused<RR><<<grid, kPatchWarps * 32, smem, ctx->stream>>>(f);                                                   \
+    } while (0)
+                if (R == 1) PATCH_FUSED(1); else if (R == 2) PATCH_FUSED(2); else if (R == 3) PATCH_FUSED(3); else PATCH_FUSED(4);
+#undef PATCH_FUSED
+            }
+            KLAUNCH_CHECK();
+            CK(ctx->h_pin.ensure(16));
+            int* hf = ctx->h_pin.as<int>();
+            CK(cudaMemcpyAsync(hf, ctx->d_pflags.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            if (hf[0] == 0 && hf[1] == 0) {
+                ctx->total = hf[3]; ctx->maxP = hf[2];
+                ctx->pack_cp = Cp;
+                ctx->patches_padded = true; ctx->pad_cap = cap;
+                const long long want = (long long)ctx->maxP + ctx->maxP / 4 + 16;
+                ctx->slab_cap = (int)std::max<long long>(want, 32);
+                ctx->have_patches = true;
+                ctx->have_unary = false;
+                ctx->fast_builds++;
+                return 0;
+            }
+        }
+    }
+    ctx->patches_padded = false;
+    ctx->exact_builds++;
     // Patches change little between outer iterations: from the second build on, the count pass stashes the members it finds
     // in a slab sized from the previous build's largest patch, and the fill pass only sorts them (no second search).  A
     // patch that outgrew the slab sends the whole build through the two-pass path again.
@@ -801,14 +871,35 @@ int msm_patch_count(msm_ctx* ctx, long long* total) {
     return 0;
 }
 
+int msm_patch_build_stats(const msm_ctx* ctx, long long* one_pass, long long* two_pass) {
+    *one_pass = ctx->fast_builds; *two_pass = ctx->exact_builds;
+    return 0;
+}
+
 int msm_get_patches(msm_ctx* ctx, int* offsets, int* idx) {
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_patches) FAIL("msm_build_patches must be called first");
     const int Ns = ctx->k_end - ctx->k_begin;
     std::vector<int> off(Ns + 1, 0);
-    if (Ns > 0) CK(cudaMemcpyAsync(off.data(), ctx->d_off.p, (size_t)(Ns + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->total > 0) CK(cudaMemcpyAsync(idx, ctx->d_idx.p, (size_t)ctx->total * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->patches_padded) {
+        // one-pass build: fixed-capacity rows in packed order; the public lists are ascending (the reference's order)
+        std::vector<int> cnt(Ns), slab((size_t)Ns * ctx->pad_cap);
+        if (Ns > 0) {
+            CK(cudaMemcpyAsync(cnt.data(), ctx->d_counts.p, (size_t)Ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(slab.data(), ctx->d_idx.p, slab.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < Ns; r++) {
+            off[r + 1] = off[r] + cnt[r];
+            int* dst = idx + off[r];
+            std::copy(slab.begin() + (size_t)r * ctx->pad_cap, slab.begin() + (size_t)r * ctx->pad_cap + cnt[r], dst);
+            std::sort(dst, dst + cnt[r]);
+        }
+    } else {
+        if (Ns > 0) CK(cudaMemcpyAsync(off.data(), ctx->d_off.p, (size_t)(Ns + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->total > 0) CK(cudaMemcpyAsync(idx, ctx->d_idx.p, (size_t)ctx->total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     for (int k = 0; k <= ctx->N; k++) {
         if (k <= ctx->k_begin) offsets[k] = 0;
         else if (k <= ctx->k_end) offsets[k] = off[k - ctx->k_begin];
@@ -873,9 +964,10 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
     UnaryArgs a;
     a.k_begin = ctx->k_begin; a.Ns = Ns; a.L = L; a.Lg = Lg; a.G = (L + Lg - 1) / Lg;
     a.off = ctx->d_off.as<int>();
+    a.cnt = ctx->patches_padded ? ctx->d_counts.as<int>() : nullptr; a.cap = ctx->pad_cap;
     a.px = ctx->d_px.as<float>(); a.py = ctx->d_py.as<float>(); a.pz = ctx->d_pz.as<float>();
     a.pa = ctx->d_pa.as<float>(); a.pw = ctx->d_pw.as<float>();
-    a.total = (int)ctx->total;
+    a.total = ctx->patches_padded ? Ns * ctx->pad_cap : (int)ctx->total;
     a.cq_rt = cq_actual;
     a.hint = hint_dev(ctx);
     a.absw = ctx->d_absw.as<float>();
@@ -884,7 +976,7 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
     a.simmeasure = ctx->par.simmeasure;
     a.out = d_out;
     a.peers = peers; a.n_full = ctx->N;
-    const size_t tot = std::max<long long>(ctx->total, 1);
+    const size_t tot = ctx->patches_padded ? (size_t)Ns * ctx->pad_cap : (size_t)std::max<long long>(ctx->total, 1);
     CK(ctx->d_pcx.ensure(tot * 4)); CK(ctx->d_pcy.ensure(tot * 4)); CK(ctx->d_pcz.ensure(tot * 4));
     CK(ctx->d_hint_face.ensure((size_t)Ns * 4));
     CK(ctx->d_lab12.ensure((size_t)Ns * L * 12 * 4));
@@ -897,7 +989,7 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
     Timer tm(ctx, "unary");
     {
         UnarySetupArgs s;
-        s.k_begin = ctx->k_begin; s.L = L; s.off = a.off; s.px = a.px; s.py = a.py; s.pz = a.pz;
+        s.k_begin = ctx->k_begin; s.L = L; s.off = a.off; s.cnt = a.cnt; s.cap = a.cap; s.px = a.px; s.py = a.py; s.pz = a.pz;
         s.Kd = ctx->d_Kd.as<double>(); s.cp = ctx->d_cp.as<double>(); s.ico = a.ico; s.hint = a.hint;
         s.hint_face = ctx->d_hint_face.as<int>(); s.lab12 = ctx->d_lab12.as<float>();
         s.tref = ctx->d_tref.as<float>();

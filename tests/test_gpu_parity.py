@@ -90,7 +90,9 @@ def test_patch_rebuild_paths_give_identical_lists(built, warp):
     ctx = pb.gpu_context(P, params=dict(rng=pb.f32(0.7)))
     ref_small = fresh(P.sxyz, P.cxyz, 0.7)
     ctx.build_patches(); same(ctx, ref_small)                 # first build: two passes
-    ctx.build_patches(); same(ctx, ref_small)                 # second build: from the slab
+    assert ctx.patch_build_stats() == (0, 1)
+    ctx.build_patches(); same(ctx, ref_small)                 # second build: one pass
+    assert ctx.patch_build_stats() == (1, 1)
     ctx.reset_source(Q.sxyz); ctx.reset_cpgrid(Q.cxyz)        # other geometry, still the slab
     ctx.build_patches(); same(ctx, fresh(Q.sxyz, Q.cxyz, 0.7))
     _set_range(ctx, P, 1.5)                                   # patches 4-5x larger than the slab: falls back
@@ -99,7 +101,18 @@ def test_patch_rebuild_paths_give_identical_lists(built, warp):
     ctx.build_patches(); same(ctx, fresh(P.sxyz, P.cxyz, 1.5))
     _set_range(ctx, P, 0.01)                                  # (nearly) empty patches through the slab
     ctx.build_patches(); same(ctx, fresh(P.sxyz, P.cxyz, 0.01))
+    one, two = ctx.patch_build_stats()
+    assert one + two == 6 and two >= 2 and one >= 3           # the range 1.5 build overflowed its rows: exact path
     ctx.close()
+    if warp == 0.0:
+        # range 1 on the undeformed icosphere: neighbours sit EXACTLY on the patch boundary — the one-pass build sees the
+        # ties, gives up, and the exact path resolves them with the reference's own formula, every time
+        c1 = pb.gpu_context(P)
+        ref1 = fresh(P.sxyz, P.cxyz, 1.0)
+        for _ in range(3):
+            c1.build_patches(); same(c1, ref1)
+        assert c1.patch_build_stats() == (0, 3)
+        c1.close()
 
 
 # ------------------------------------------------------------------------------------------------ unary
