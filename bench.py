@@ -12,6 +12,8 @@ N*B subjects with no data-path collective ("weak" scaling, SURVEY.md §8e row "b
 state exceed the 126 MB L2, so successive timed iterations do not find their inputs in L2.
 
   value : evaluations / second, inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks.
+          The step is LIKE FOR LIKE with the reference arm: patch construction (get_source_data) + the whole unary table +
+          the all-label fusion-move triplet costs.  value_tables_only (both arms) leaves the patch construction out.
   e2e   : the same step through the reference-facing host classes (NonLinearSRegDiscreteModel::reset_meshspace ->
           setupCostFunction [patch construction + unary table] -> triplet moves) with pinned HOST buffers in and out;
           the B independent subjects of a GPU are driven by --e2e-threads host threads, one private stream each
@@ -276,8 +278,38 @@ def cpu_sample(data_level, cp_level, C, rows, threads, steps=1, warmup=0):
     return r, kind, sample
 
 
+# ---------------------------------------------------------------------------------------------- per-level wall time
+def level_wall(data_level, cp_level, C, arm, threads):
+    """Second half of BASELINE's metric: wall time of ONE resolution level (one outer iteration: cost evaluation + the
+    reference's HOCR optimiser + label application + source warp), restating Mesh_registration::run_discrete_opt
+    (src/mesh_registration.cpp:316-397) as tests/level_walltime.py does.  arm "gpu": this repository's cost functions and
+    host classes; the OPTIMISER is the reference's own unmodified Fusion / ELC / FastPD code in both arms (it stays on the
+    host by north_star; compiled in place into oracle/_ref, which is why this figure is only produced where that exists).
+    arm "reference": the reference's own cost functions as well, one host thread (more is a data race in it)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import level_walltime as lw
+    import problems as pb
+    P = pb.make_problem(data_level, cp_level, C, seed=51, warp=0.0)
+    P.seed = 51
+    run = lw.run_gpu if arm == "gpu" else lw.run_reference
+    if arm == "gpu":   # the table-aware fusion driver (host/src/FusionTables.h): same labellings as Fusion::optimize, batched tables
+        os.environ["MSM_HOCR_DRIVER"] = "tables"
+    t0 = time.perf_counter()
+    try:
+        src, labs, rep = run(P, [cp_level], 1, C, threads, f32(0.1))
+    finally:
+        os.environ.pop("MSM_HOCR_DRIVER", None)
+    r = rep[0]
+    return {"level": f"ico{data_level} data / ico{cp_level} control grid, C={C}, strain regulariser, HOCR, 1 outer iteration", "arm": arm,
+            "level_wall_s": r["level_wall_s"], "setup_s": r["setup_s"], "cost_eval_s": r["cost_eval_s"], "optimiser_s": r["optimiser_s"],
+            "warp_s": r["warp_s"], "labels_changed": int((labs[0][0] != 0).sum()), "N": r["N"], "host_threads": threads if arm == "gpu" else 1,
+            "total_s": time.perf_counter() - t0,
+            "optimiser": ("FusionTables driver over the reference's unmodified ELC.h / FastPD.h cores (batched move tables, flat binary MRF)"
+                          if arm == "gpu" else "reference Fusion.h / ELC.h / FastPD.h, unmodified")}
+
+
 # ---------------------------------------------------------------------------------------------- CP-sharded mode
-def bench_cp_sharded(args, rank, world, local, C, metric, unit):
+def bench_cp_sharded(args, rank, world, local, C, metric, unit, emit=True):
     """ONE HCP-scale registration (ico7 / ico5): control points and triplets split into contiguous ranges over the GPUs
     (SURVEY.md §8e rows 1-2), every GPU holds the replicated meshes, table slices gathered with one NCCL all_gather each
     per step (never inside a per-label loop).  Strong scaling: total work fixed."""
@@ -377,8 +409,9 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
     ms_per_step = float(t.item()) / args.steps
     evals = N * L + L * T * 8
     checksum = float(U.double().sum().item()), float(M.double().sum().item())
+    line = None
     if rank == 0:
-        emit_line(json.dumps({
+        line = ({
             "metric": metric, "value": evals / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (unary) / f64 (triplet)", "data": "synthetic",
@@ -389,13 +422,18 @@ def bench_cp_sharded(args, rank, world, local, C, metric, unit):
                                       + ", one device-side barrier per step)" + why if exchange in ("p2p", "mc") else "gathered with NCCL all_gather" + why),
                        "exchange": exchange, "N": N, "L": L, "T": T, "gathered_bytes_per_step": 4 * (L * N + L * T * 8),
                        "l2": "single subject: inputs are L2 resident between steps (mode used to show the sharded path, not the headline)"},
-            "gpu_launches": int(ctx.launch_count() - launches0), "checksum": checksum}))
-    if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+            "gpu_launches": int(ctx.launch_count() - launches0), "checksum": checksum})
+    m.close()
+    if emit:
+        if rank == 0:
+            emit_line(json.dumps(line))
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+    return line
 
 
 # ---------------------------------------------------------------------------------------------- groupwise mode
-def bench_group(args, rank, world, local, metric, unit):
+def bench_group(args, rank, world, local, metric, unit, emit=True):
     """BASELINE.json configs[4]: groupwise registration (DiscreteGroupModel) of S subjects with group triplet costs
     (src/DiscreteGroupCostFunction.cpp:9-30), subjects sharded over the GPUs.  The S control meshes are replicated (S*N
     points, small); each GPU evaluates the fusion-move triplet costs of every label for ITS subjects' triangles and stores
@@ -479,18 +517,23 @@ def bench_group(args, rank, world, local, metric, unit):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     evals = L * S * T * 8
+    line = None
     if rank == 0:
-        emit_line(json.dumps({
+        line = ({
             "metric": metric, "value": evals / (ms_per_step * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"groupwise (BASELINE.json configs[4]): {S} subjects, ico{lvl} control grids ({N} points, {T} triangles each), "
                                    f"L={L}; step = group fusion-move triplet costs of every label, subjects sharded over {world} GPU(s), table "
                                    f"assembled on every rank by " + ("an NCCL all-gather" + why if nccl_gather else ("NVSwitch multicast stores" if mc else "peer stores") + " (fused exchange)"),
                        "S": S, "N": N, "T": T, "L": L, "table_bytes": 4 * evals, "checksum": checksum},
-            "gpu_launches": int(ctx.launch_count() - launches0)}))
+            "gpu_launches": int(ctx.launch_count() - launches0)})
     ctx.close()
-    if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+    if emit:
+        if rank == 0:
+            emit_line(json.dumps(line))
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+    return line
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -511,6 +554,12 @@ def main():
                     help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
                          "and triplets sharded over the GPUs (strong scaling); group: groupwise registration "
                          "(DiscreteGroupCostFunction triplet costs of --group-subjects subjects, subjects sharded over the GPUs)")
+    ap.add_argument("--level-wall", type=int, default=1,
+                    help="1: also time one resolution level end to end (one outer iteration; N = 1 only; needs oracle/_ref for the "
+                         "reference's optimiser); 0: skip")
+    ap.add_argument("--secondary", type=int, default=1,
+                    help="1: after the headline measurement also run the CP-sharded (configs[2] as written) and groupwise (configs[4]) "
+                         "steps on the same GPUs and attach them as `secondary`; 0: skip")
     ap.add_argument("--group-subjects", type=int, default=16)
     ap.add_argument("--group-cp-level", type=int, default=4)
     ap.add_argument("--cp-exchange", default="mc", choices=["mc", "p2p", "nccl"],
@@ -524,7 +573,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     C = args.channels
     workload = (f"C3 (BASELINE.json configs[2]): ico{args.data_level} data x ico{args.cp_level} control grid, L=19 labels, C={C}, "
-                f"range 1, Pearson; step = unary table + all-label fusion-move triplet costs for {args.subjects_per_gpu} independent subjects per GPU")
+                f"range 1, Pearson; step = patch construction + unary table + all-label fusion-move triplet costs for {args.subjects_per_gpu} independent subjects per GPU")
     metric, unit = "unary+triplet cost evals/s", "evals/s"
 
     # ------------------------------------------------------------------ reference (CPU) arm
@@ -545,7 +594,13 @@ def main():
                 "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": kind, "sample": sample,
                                  "value_tables_only": r["evals_per_s_resident"], "t_patches_s": r["t_patches"], "t_unary_s": r["t_unary"],
                                  "t_triplet_s": r["t_triplet"]},
-                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+                "value_tables_only": r["evals_per_s_resident"]}
+        if args.level_wall and kind == "reference":
+            try:
+                line["level_wall"] = level_wall(args.data_level, args.cp_level, C, "reference", 1)
+            except Exception as e:
+                line["level_wall"] = {"error": f"{type(e).__name__}: {e}"}
         emit_line(json.dumps(line))
         return
 
@@ -608,8 +663,10 @@ def main():
         alg_bytes_unary.append(int((P * ((48 + 12 * C) * L + (16 + 8 * C)) + 8 * L).sum()))
         patch_totals.append(int(P.sum()))
 
-    def resident_step():
+    def resident_step(with_patches=True):
         for s in range(B):
+            if with_patches:
+                ctxs[s].build_patches()                      # get_source_data: patches of the (device-resident) source / control grid
             ctxs[s].unary_table_dev(d_unary[s].data_ptr())
             ctxs[s].triplet_moves_dev(lab_dev.data_ptr(), -1, d_moves[s].data_ptr())
 
@@ -619,9 +676,23 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        sync_all()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
     for _ in range(args.warmup):
         resident_step()
     sync_all()
+    ms_tables_only = timed(lambda: resident_step(False), args.steps)      # secondary: tables only (no patch construction)
     launches0 = sum(c.launch_count() for c in ctxs)
     for c in ctxs:
         c.set_timing(2)
@@ -629,28 +700,46 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record(stream)
-    for _ in range(args.steps):
-        resident_step()
-    e1.record(stream)
-    sync_all()
-    ms_total = e0.elapsed_time(e1)
+    ms_per_step = timed(resident_step, args.steps)                          # headline: patches + unary table + fusion moves
     launches = sum(c.launch_count() for c in ctxs) - launches0
-    um, un = 0.0, 0
-    tm_, tn_ = 0.0, 0
+    fam = {}
     for c in ctxs:
-        a, b = c.timing_collect("unary_main"); um += a; un += b
-        a, b = c.timing_collect("triplet_moves"); tm_ += a; tn_ += b
-        c.timing_collect("unary"); c.set_timing(0)
+        for f in ("unary_main", "triplet_moves", "patches", "unary"):
+            a_, b_ = c.timing_collect(f)
+            fam.setdefault(f, [0.0, 0]); fam[f][0] += a_; fam[f][1] += b_
+        c.set_timing(0)
+    um, un = fam["unary_main"]; tm_, tn_ = fam["triplet_moves"]
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
     value = evals_per_subject * B * world / (ms_per_step * 1e-3)
+    value_tables_only = evals_per_subject * B * world / (ms_tables_only * 1e-3)
+    one_pass = [c.patch_build_stats() for c in ctxs]
+
+    # ---- the triplet kernels against their byte model ((84/k) + 4 B per evaluation; k = 8 per fusion move,
+    # k = L^3 for the full look-up table that serves the unmodified Fusion::optimize)
+    trip_roof = None
+    if rank == 0:
+        try:
+            c0 = ctxs[0]
+            c0.set_timing(1)
+            full = torch.empty((T, L, L, L), dtype=torch.float32, device="cuda")
+            tt = []
+            for _ in range(5):
+                c0.triplet_table_dev(0, T, full.data_ptr()); tt.append(c0.last_kernel_ms("triplet_table"))
+            mm = []
+            for _ in range(5):
+                c0.triplet_moves_dev(lab_dev.data_ptr(), -1, d_moves[0].data_ptr()); mm.append(c0.last_kernel_ms("triplet_moves"))
+            c0.set_timing(0)
+            del full
+            peak_, _src = measured_peak()
+            tb, mb = (84.0 / L ** 3 + 4.0) * T * L ** 3, (84.0 / 8 + 4.0) * T * L * 8
+            trip_roof = {"bound": "hbm", "unit": "GB/s", "peak": peak_,
+                         "table": {"kernel": "k_triplet_prep + k_triplet_table_fast", "evals": T * L ** 3, "algorithmic_bytes": tb, "ms": min(tt),
+                                   "achieved": tb / (min(tt) * 1e-3) / 1e9, "frac": tb / (min(tt) * 1e-3) / 1e9 / peak_},
+                         "moves": {"kernel": "k_triplet_moves_fast", "evals": T * L * 8, "algorithmic_bytes": mb, "ms": min(mm),
+                                   "achieved": mb / (min(mm) * 1e-3) / 1e9, "frac": mb / (min(mm) * 1e-3) / 1e9 / peak_},
+                         "note": "best of 5 launches each, one subject, CUDA events on the launching stream (msm_set_timing 1)"}
+        except Exception as e:
+            trip_roof = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- end to end through the host classes, host buffers in/out
     # The B subjects of a GPU are independent registrations: each one is driven by its own host thread on its context's
@@ -735,6 +824,11 @@ def main():
                     "host_threads": e2e_threads, "value_one_host_thread": e2e_serial,
                     "api": "NonLinearSRegDiscreteModel::reset_meshspace/reset_CPgrid/setupCostFunction + computeTripletMoves"},
             "gpu_launches": int(launches), "clocks": clocks,
+            "value_tables_only": value_tables_only, "ms_per_step_tables_only": ms_tables_only,
+            "step": "per subject: get_source_data (patch construction, one-pass path) + whole unary table + all-label fusion-move triplet costs",
+            "kernel_ms_per_subject": {f: (v[0] / v[1] if v[1] else None) for f, v in fam.items()},
+            "patch_builds_one_pass_vs_exact": [sum(x[0] for x in one_pass), sum(x[1] for x in one_pass)],
+            "roofline_triplet": trip_roof,
         }
         if world == 1:
             try:
@@ -744,6 +838,31 @@ def main():
                                         "value_tables_only": r["evals_per_s_resident"]}
             except Exception as e:
                 line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    else:
+        line = None
+    # ---- secondary: the other sharded configurations of BASELINE.json on the same GPUs (all ranks take part)
+    secondary = {}
+    if args.secondary:
+        for m_ in models:
+            m_.close()
+        models.clear(); ctxs.clear()
+        torch.cuda.empty_cache()
+        for name, fn in (("cp_sharded", lambda: bench_cp_sharded(args, rank, world, local, C, metric, unit, emit=False)),
+                         ("groupwise", lambda: bench_group(args, rank, world, local, metric, unit, emit=False))):
+            try:
+                secondary[name] = fn()
+            except Exception as e:
+                secondary[name] = {"error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                dist.barrier()
+    if rank == 0:
+        if secondary:
+            line["secondary"] = secondary
+        if args.level_wall and world == 1:
+            try:
+                line["level_wall"] = level_wall(args.data_level, args.cp_level, C, "gpu", os.cpu_count() or 1)
+            except Exception as e:
+                line["level_wall"] = {"error": f"{type(e).__name__}: {e}"}
         emit_line(json.dumps(line))
     if world > 1:
         dist.barrier()

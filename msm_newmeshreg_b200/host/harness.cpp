@@ -541,6 +541,13 @@ int ref_run_discrete_opt(void* h, int iters, int threads, double* source_xyz, in
                 newenergy = opt.run();
                 opt.getLabeling(b->model->getLabeling());
             } else if (dopt == "HOCR") {
+#ifndef WITH_REF_COST
+                // MSM_HOCR_DRIVER=tables: the table-aware fusion driver (src/FusionTables.h: batched GPU move tables, flat
+                // binary MRF) in place of the reference's Fusion::optimize; same labellings (tests/test_gpu_model.py)
+                const char* drv = std::getenv("MSM_HOCR_DRIVER");
+                if (drv && std::string(drv) == "tables") newenergy = FusionTables::optimize(b->model, false, threads);
+                else
+#endif
                 newenergy = Fusion::optimize(b->model, false, threads);
             } else throw MeshregException("Unrecognized optimiser");
             double t2 = omp_get_wtime();

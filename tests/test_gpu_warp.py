@@ -162,3 +162,23 @@ def test_large_patches_from_concurrent_host_threads(built):
             threaded = list(pool.map(run, probs))
         for a, b in zip(serial, threaded):
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+def test_run_discrete_opt_with_the_table_aware_driver_gives_the_same_registration(built, monkeypatch):
+    """MSM_HOCR_DRIVER=tables swaps Fusion::optimize for host/src/FusionTables.h (batched GPU move tables, flat binary MRF
+    in front of the reference's unchanged ELC / FastPD cores) inside the run_discrete_opt loop: same labellings at every
+    outer iteration, same warped sphere."""
+    from msm_newmeshreg_b200 import host
+    P = pb.make_problem(5, 3, 1, seed=33, warp=0.0)
+    out = []
+    for drv in ("fusion", "tables"):
+        monkeypatch.setenv("MSM_HOCR_DRIVER", drv)
+        pr = dict(pb.DEFAULT_PARAMS); pr.update(rmode=3, dopt="HOCR")
+        m = host.Model(sgres=5, cpres=3, multivariate=False, _lib_override=pyref.lib(), threads=4, **pr)
+        m.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref); m.initialize()
+        src, labs, en, tm = pyref.run_discrete_opt(m, P.txyz, 3, threads=4)
+        out.append((src, labs, en)); m.close()
+    assert out[0][1].shape == out[1][1].shape and np.array_equal(out[0][1], out[1][1])
+    assert np.abs(out[0][0] - out[1][0]).max() < 1e-9 and np.allclose(out[0][2], out[1][2], rtol=1e-6)

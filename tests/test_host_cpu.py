@@ -152,6 +152,11 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"] > 0
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
     assert "workload" in d["config"]
+    assert d["value_tables_only"] >= d["value"]                        # like for like with the GPU arm: value includes the patch search
+    if d["cpu_baseline"]["kind"] == "reference":                        # one whole resolution level through the reference itself
+        lw = d["level_wall"]
+        assert "error" not in lw, lw
+        assert lw["arm"] == "reference" and lw["level_wall_s"] > 0 and lw["N"] == 642
 
 
 # ------------------------------------------------------------------------------------------------ hierarchy builder (CPU)
