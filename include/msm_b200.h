@@ -150,6 +150,9 @@ int msm_pair_table_dev(msm_ctx* ctx, float* d_out);
 int msm_set_group_patches(msm_ctx* ctx, long long nmaps, const long long* off, const int* keys, const double* vals);
 int msm_group_pair_costs(msm_ctx* ctx, int n, const int* q, double* out);
 int msm_group_pair_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out);
+/*  _table : the whole float[P][L][L] table, layout pair*L*L + labelB*L + labelA (src/DiscreteCostFunction.cpp:303): serves
+ *           computePairwiseCost of the unmodified Fusion::optimize as a look-up */
+int msm_group_pair_table(msm_ctx* ctx, float* out);
 
 /* Octree::get_closest_triangle + barycentric weights on the target ([EXT] A3/A4; call sites
  * src/DiscreteCostFunction.cpp:421-433).  tri = index into the `tris` given to msm_set_target; w double[M][3]

@@ -821,6 +821,17 @@ __global__ void __launch_bounds__(128) k_group_pair_queries(GroupPairArgs a, int
     out[i] = group_pair_cost(a, q[3 * i], q[3 * i + 1], q[3 * i + 2]);
 }
 
+// the whole [P][L][L] table in the reference's pairwise layout (pair*L*L + labelB*L + labelA): serves the per-element
+// virtual of the unmodified Fusion::optimize as a look-up
+__global__ void __launch_bounds__(128) k_group_pair_table(GroupPairArgs a, int P, float* __restrict__ out) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int L2 = a.L * a.L;
+    if (gid >= (long long)P * L2) return;
+    const int pr = (int)(gid / L2), r = (int)(gid - (long long)pr * L2);
+    const int lb = r / a.L, la = r - lb * a.L;
+    out[gid] = (float)group_pair_cost(a, pr, la, lb);
+}
+
 // fusion-move costs of include/Fusion/Fusion.h:169-172: (cur,cur) (cur,alpha) (alpha,cur) (alpha,alpha) per pair
 __global__ void __launch_bounds__(128) k_group_pair_moves(GroupPairArgs a, int P, const int* __restrict__ labeling, int alpha,
                                                           double* __restrict__ out) {

@@ -1283,6 +1283,22 @@ int msm_group_pair_costs(msm_ctx* ctx, int n, const int* q, double* out) {
     return 0;
 }
 
+int msm_group_pair_table(msm_ctx* ctx, float* out) {
+    CK(cudaSetDevice(ctx->device));
+    GroupPairArgs a;
+    if (group_pair_args(ctx, a)) return 1;
+    const long long n = (long long)ctx->P * ctx->L * ctx->L;
+    CK(ctx->d_scratch2.ensure((size_t)n * 4));
+    {
+        Timer tm(ctx, "group_pair");
+        k_group_pair_table<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, ctx->P, ctx->d_scratch2.as<float>());
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_scratch2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int msm_group_pair_moves(msm_ctx* ctx, const int* labeling, int alpha, double* out) {
     CK(cudaSetDevice(ctx->device));
     GroupPairArgs a;

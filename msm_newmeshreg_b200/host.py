@@ -74,6 +74,18 @@ def mesh_interpolate(up, init_xyz, tris, final_xyz, _lib_override=None):
     return up
 
 
+def metric_resample(in_xyz, in_tris, values, ref_xyz, ref_tris, _lib_override=None):
+    """newresampler::metric_resample ([EXT] A8, adaptive barycentric): values[d][v_in] on mesh `in` -> [d][v_ref] on mesh
+    `ref`; both batches of point locations on the GPU."""
+    L = _lib_override or lib()
+    in_xyz, p1 = _d(in_xyz); in_tris, p2 = _i(in_tris); values = np.atleast_2d(values); values, p3 = _d(values)
+    ref_xyz, p4 = _d(ref_xyz); ref_tris, p5 = _i(ref_tris)
+    out = np.empty((values.shape[0], len(ref_xyz)))
+    if L.msmhost_metric_resample(p1, len(in_xyz), p2, len(in_tris), p3, values.shape[0], p4, len(ref_xyz), p5, len(ref_tris), out.ctypes.data_as(c_dp)) != 0:
+        raise HostError(L.msmhost_last_error().decode())
+    return out
+
+
 def unfold(xyz, tris, _lib_override=None):
     """newmeshreg::unfold (src/reg_tools.cpp:134-181), host side."""
     L = _lib_override or lib()
@@ -184,3 +196,101 @@ class Model:
         else:
             self._ck(self._L.msmhost_model_triplet_moves(self.h, p, int(alpha), out.ctypes.data_as(c_dp)))
         return out
+
+
+class GroupModel:
+    """DiscreteGroupModel (+ its GPU-backed DiscreteGroupCostFunction) behind the harness: the call sequence of
+    Group_Mesh_registration (src/group_mesh_registration.cpp:20-36,49-108).  Global node id = subject * N_subj + vertex."""
+
+    def __init__(self, lam=0.1, rexp=2.0, mu=0.4, kappa=1.6, rng=1.0, sgres=4, cpres=2, labeldist=0.5, threads=1, _lib_override=None):
+        self._L = _lib_override or lib()
+        self._L.msmhost_group_create.restype = C.c_void_p
+        self._L.msmhost_group_create.argtypes = [C.c_double] * 5 + [C.c_int, C.c_int, C.c_double, C.c_int]
+        self._L.msmhost_group_total.restype = C.c_double
+        h = self._L.msmhost_group_create(lam, rexp, mu, kappa, rng, sgres, cpres, labeldist, threads)
+        if not h:
+            raise HostError(self._L.msmhost_last_error().decode())
+        self.h = C.c_void_p(h)
+        self.cpres = cpres
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.msmhost_group_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            raise HostError(self._L.msmhost_last_error().decode())
+
+    def set_data(self, txyz, ttris, data):
+        """template icosphere + data[s][v]: one feature row per subject on the template's vertices."""
+        txyz, p1 = _d(txyz); ttris, p2 = _i(ttris); data = np.atleast_2d(data); data, p3 = _d(data)
+        assert data.shape[1] == len(txyz)
+        self.S, self.Vt = data.shape[0], len(txyz)
+        self._ck(self._L.msmhost_group_set_data(self.h, p1, len(txyz), p2, len(ttris), self.S, p3))
+
+    def initialize(self):
+        self._ck(self._L.msmhost_group_initialize(self.h, self.cpres)); self._sizes()
+
+    def _sizes(self):
+        n, l, p, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._L.msmhost_group_sizes(self.h, C.byref(n), C.byref(l), C.byref(p), C.byref(t))
+        self.N, self.L, self.P, self.T = n.value, l.value, p.value, t.value
+        self.N_subj = self.N // max(self.S, 1)
+
+    def reset_meshspace(self, subject, xyz):
+        xyz, p = _d(xyz); self._ck(self._L.msmhost_group_reset_meshspace(self.h, int(subject), p))
+
+    def reset_cpgrid(self, subject, xyz):
+        xyz, p = _d(xyz); self._ck(self._L.msmhost_group_reset_cpgrid(self.h, int(subject), p))
+
+    def setup(self):
+        self._ck(self._L.msmhost_group_setup(self.h)); self._sizes()
+
+    def cpgrids(self):
+        out = np.empty((self.S, self.N_subj, 3)); self._ck(self._L.msmhost_group_get(self.h, out.ctypes.data_as(c_dp), None, None, None)); return out
+
+    def labels(self):
+        out = np.empty((self.L, 3)); self._ck(self._L.msmhost_group_get(self.h, None, out.ctypes.data_as(c_dp), None, None)); return out
+
+    def pairs(self):
+        out = np.empty((self.P, 2), np.int32); self._ck(self._L.msmhost_group_get(self.h, None, None, out.ctypes.data_as(c_ip), None)); return out
+
+    def triplets(self):
+        out = np.empty((self.T, 3), np.int32); self._ck(self._L.msmhost_group_get(self.h, None, None, None, out.ctypes.data_as(c_ip))); return out
+
+    def costs(self, kind, q):
+        q, pq = _i(q); out = np.empty(len(q))
+        self._ck(self._L.msmhost_group_costs(self.h, {"pair": 1, "triplet": 2}[kind], len(q), pq, out.ctypes.data_as(c_dp)))
+        return out
+
+    def set_labeling(self, lab):
+        lab, p = _i(lab); self._L.msmhost_group_set_labeling(self.h, p)
+
+    def labeling(self):
+        out = np.empty(self.N, np.int32); self._L.msmhost_group_get_labeling(self.h, out.ctypes.data_as(c_ip)); return out
+
+    def total(self):
+        return float(self._L.msmhost_group_total(self.h))
+
+    def apply_labeling(self):
+        out = np.empty((self.S, self.N_subj, 3)); self._ck(self._L.msmhost_group_apply_labeling(self.h, out.ctypes.data_as(c_dp))); return out
+
+    def rotated_values(self, subject, label):
+        """rotated_meshes[subject * L + label] (src/DiscreteGroupModel.cpp:92) on the template's vertices (product mirror only)."""
+        out = np.empty(self.Vt)
+        self._ck(self._L.msmhost_group_rotated(self.h, int(subject), int(label), out.ctypes.data_as(c_dp)))
+        return out
+
+    def fusion(self, threads=1, tables=False):
+        """Fusion::optimize (the reference's, unmodified) or, tables=True, the batched FusionTables::optimize_group — only
+        in libraries built with the reference's optimisers (oracle/_ref)."""
+        e = C.c_double()
+        f = self._L.ref_fusion_tables_group if tables else self._L.ref_fusion_group
+        self._ck(f(self.h, int(threads), C.byref(e)))
+        return self.labeling(), e.value

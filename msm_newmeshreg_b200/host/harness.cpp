@@ -355,6 +355,167 @@ int msmhost_unfold(double* xyz, int nv, const int* tris, int nf) {
     });
 }
 
+// ---- DiscreteGroupModel (src/DiscreteGroupModel.{h,cpp}) behind the same kind of flat interface: the call sequence of
+// Group_Mesh_registration (src/group_mesh_registration.cpp:20-36,49-108): set_featurespace / set_meshspace(template, SPH_orig, S) /
+// Initialize(control) once, then per outer iteration reset_meshspace(subject mesh) ... setupCostFunction() -> optimise ->
+// applyLabeling().  Compiled for the product mirror (GPU-backed) and, with -DWITH_REF_COST, for the reference's own classes.
+namespace {
+#ifdef WITH_REF_COST
+struct GroupModelT : DiscreteGroupModel {
+    using DiscreteGroupModel::DiscreteGroupModel;
+    const std::vector<newresampler::Point>& get_labels() const { return m_labels; }
+};
+std::shared_ptr<featurespace> make_group_features(const double* data, int S, int V) {
+    std::vector<std::string> keys;
+    for (int s = 0; s < S; s++) {
+        auto M = std::make_shared<MISCMATHS::FullBFMatrix>(1, V);
+        for (int v = 0; v < V; v++) M->Set(1, v + 1, data[(size_t)s * V + v]);
+        keys.push_back("harness:subject-" + std::to_string(s));
+        refcost::feature_registry()[keys.back()] = M;
+    }
+    return std::make_shared<featurespace>(keys);
+}
+#else
+using GroupModelT = DiscreteGroupModel;
+std::shared_ptr<featurespace> make_group_features(const double* data, int S, int V) {
+    auto f = std::make_shared<featurespace>();
+    for (int s = 0; s < S; s++) f->add_subject(data + (size_t)s * V, V);
+    return f;
+}
+#endif
+struct GroupModelBox {
+    std::shared_ptr<GroupModelT> model;
+    myparam params;
+    newresampler::Mesh templ;
+    int S = 0;
+};
+}  // namespace
+
+void* msmhost_group_create(double lambda, double rexp, double mu, double kappa, double range, int sgres, int cpres, double labeldist, int threads) {
+    auto* b = new GroupModelBox();
+    b->params = default_parameters();
+    myparam& P = b->params;
+    P["lambda"] = (float)lambda; P["exponent"] = (float)rexp; P["shearmodulus"] = (float)mu; P["bulkmodulus"] = (float)kappa;
+    P["range"] = (float)range; P["regularisermode"] = 3; P["SGres"] = sgres; P["CPres"] = cpres; P["labeldist"] = (float)labeldist;
+    P["multivariate"] = false; P["dOPT"] = std::string("HOCR"); P["numthreads"] = threads;
+    if (guard([&] { b->model = std::make_shared<GroupModelT>(P); })) { delete b; return nullptr; }
+    return b;
+}
+void msmhost_group_destroy(void* h) { delete (GroupModelBox*)h; }
+// template mesh (a regular icosphere), S subjects, per-subject data on that icosphere's vertices: data[s][v]
+int msmhost_group_set_data(void* h, const double* txyz, int Vt, const int* ttris, int Ft, int S, const double* data) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        b->templ = mesh_from(txyz, Vt, ttris, Ft);
+        b->S = S;
+        b->model->set_featurespace(make_group_features(data, S, Vt));
+        b->model->set_meshspace(b->templ, b->templ, S);
+    });
+}
+int msmhost_group_initialize(void* h, int cpres) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        newresampler::Mesh CONTROL = newresampler::make_mesh_from_icosa(cpres);
+        newresampler::recentre(CONTROL);
+        newresampler::true_rescale(CONTROL, RAD);
+        b->model->Initialize(CONTROL);
+    });
+}
+int msmhost_group_sizes(void* h, int* N, int* L, int* P, int* T) {
+    auto* b = (GroupModelBox*)h;
+    *N = b->model->getNumNodes(); *L = b->model->getNumLabels(); *P = b->model->getNumPairs(); *T = b->model->getNumTriplets();
+    return 0;
+}
+int msmhost_group_reset_meshspace(void* h, int subject, const double* xyz) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        newresampler::Mesh m = b->templ;
+        assign_coords(m, xyz);
+        b->model->reset_meshspace(m, subject);
+    });
+}
+int msmhost_group_reset_cpgrid(void* h, int subject, const double* xyz) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        newresampler::Mesh g = b->model->get_CPgrid(subject);
+        assign_coords(g, xyz);
+        b->model->reset_CPgrid(g, subject);
+    });
+}
+int msmhost_group_setup(void* h) { auto* b = (GroupModelBox*)h; return guard([&] { b->model->setupCostFunction(); }); }
+int msmhost_group_get(void* h, double* cpgrids /*[S][N][3]*/, double* labels, int* pairs, int* triplets) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        if (cpgrids) {
+            size_t o = 0;
+            for (int s = 0; s < b->S; s++) { auto c = coords_of(b->model->get_CPgrid(s)); std::memcpy(cpgrids + o, c.data(), c.size() * sizeof(double)); o += c.size(); }
+        }
+        if (labels) {
+            const auto& l = b->model->get_labels();
+            for (size_t i = 0; i < l.size(); i++) { labels[3 * i] = l[i].X; labels[3 * i + 1] = l[i].Y; labels[3 * i + 2] = l[i].Z; }
+        }
+        if (pairs && b->model->getNumPairs()) std::memcpy(pairs, b->model->getPairs(), sizeof(int) * 2 * b->model->getNumPairs());
+        if (triplets && b->model->getNumTriplets()) std::memcpy(triplets, b->model->getTriplets(), sizeof(int) * 3 * b->model->getNumTriplets());
+    });
+}
+// per-element virtuals, batched: kind 1 pairwise (q[n][3]), 2 triplet (q[n][4])
+int msmhost_group_costs(void* h, int kind, int n, const int* q, double* out) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        for (int i = 0; i < n; i++) {
+            if (kind == 1) out[i] = b->model->computePairwiseCost(q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+            else out[i] = b->model->computeTripletCost(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]);
+        }
+    });
+}
+int msmhost_group_set_labeling(void* h, const int* lab) {
+    auto* b = (GroupModelBox*)h;
+    std::memcpy(b->model->getLabeling(), lab, sizeof(int) * b->model->getNumNodes());
+    return 0;
+}
+int msmhost_group_get_labeling(void* h, int* lab) {
+    auto* b = (GroupModelBox*)h;
+    std::memcpy(lab, b->model->getLabeling(), sizeof(int) * b->model->getNumNodes());
+    return 0;
+}
+double msmhost_group_total(void* h) { auto* b = (GroupModelBox*)h; double v = 0; guard([&] { v = b->model->evaluateTotalCostSum(); }); return v; }
+int msmhost_group_apply_labeling(void* h, double* cpgrids) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        b->model->applyLabeling();
+        size_t o = 0;
+        for (int s = 0; s < b->S; s++) { auto c = coords_of(b->model->get_CPgrid(s)); std::memcpy(cpgrids + o, c.data(), c.size() * sizeof(double)); o += c.size(); }
+    });
+}
+#ifndef WITH_REF_COST
+// rotated_meshes[subject * L + label] (src/DiscreteGroupModel.cpp:92), first data row, on the template's vertices
+int msmhost_group_rotated(void* h, int subject, int label, double* out) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] { const auto& v = b->model->rotated_mesh_values(subject, label); std::memcpy(out, v.data(), v.size() * sizeof(double)); });
+}
+// newresampler::metric_resample on raw arrays ([EXT] A8): values[d][v_in] -> out[d][v_ref]
+int msmhost_metric_resample(const double* in_xyz, int nv_in, const int* in_tris, int nf_in, const double* values, int dims, const double* ref_xyz,
+                            int nv_ref, const int* ref_tris, int nf_ref, double* out) {
+    return guard([&] {
+        const newresampler::Mesh A = mesh_from(in_xyz, nv_in, in_tris, nf_in), B = mesh_from(ref_xyz, nv_ref, ref_tris, nf_ref);
+        const std::vector<double> r = newresampler::metric_resample(A, values, dims, B);
+        std::memcpy(out, r.data(), r.size() * sizeof(double));
+    });
+}
+#endif
+#ifdef WITH_REF_OPTIM
+int ref_fusion_group(void* h, int threads, double* energy) {   // src/group_mesh_registration.cpp:74
+    auto* b = (GroupModelBox*)h;
+    return guard([&] { *energy = Fusion::optimize(b->model, false, threads); });
+}
+#ifndef WITH_REF_COST
+int ref_fusion_tables_group(void* h, int threads, double* energy) {   // host/src/FusionTables.h optimize_group: batched GPU tables
+    auto* b = (GroupModelBox*)h;
+    return guard([&] { *energy = FusionTables::optimize_group(b->model, false, threads); });
+}
+#endif
+#endif
+
 #ifdef WITH_REF_COST
 // ---- the reference's DiscreteGroupCostFunction (src/DiscreteGroupCostFunction.{h,cpp}), same flat interface as the
 // oracle port's orc_gc_* (oracle/oracle_capi.cpp) so the two can be compared query by query -----------------------------

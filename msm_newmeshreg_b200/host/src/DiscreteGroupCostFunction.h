@@ -32,6 +32,7 @@ public:
             moff[m + 1] = (long long)mkey.size();
         }
         patches_dirty = true;
+        pair_epoch = -1;
     }
     // CSR variant for producers that never materialise std::map (keys ascending within a map)
     void set_patch_data_csr(const long long* off, long long nmaps, const int* keys, const double* vals) {
@@ -39,6 +40,7 @@ public:
         mkey.assign(keys, keys + off[nmaps]);
         mval.assign(vals, vals + off[nmaps]);
         patches_dirty = true;
+        pair_epoch = -1;
     }
 
     void get_source_data() override {}                       // no unary term (src/DiscreteCostFunction.h:34)
@@ -50,18 +52,26 @@ public:
         const size_t L = m_num_labels;
         return (double)triplet_table[(((size_t)triplet * L + labelA) * L + labelB) * L + labelC];
     }
-    double computePairwiseCost(int pair, int labelA, int labelB) override {  // one query (batched variants below)
-        push_patches();
-        const int q[3] = {pair, labelA, labelB};
-        double out = 0;
-        std::lock_guard<std::mutex> lock(lazy);
-        check(msm_group_pair_costs(ctx, 1, q, &out));
-        return out;
+    // The per-element virtual of the unmodified Fusion::optimize (4 P calls per proposal label from an OpenMP loop,
+    // include/Fusion/Fusion.h:163-172) is a look-up in the [P][L][L] table of the current outer iteration, built on the GPU at
+    // first use; table-aware drivers use the batched entry points below instead and never build it.
+    double computePairwiseCost(int pair, int labelA, int labelB) override {
+        ensure_group_pair_table();
+        return (double)pair_table[((size_t)pair * m_num_labels + labelB) * m_num_labels + labelA];
     }
     void computePairwiseCosts(const int*) override {}
     // batched paths for a table-aware fusion driver
-    void computePairwiseQueries(int n, const int* q, double* out) { push_patches(); check(msm_group_pair_costs(ctx, n, q, out)); }
-    void computePairwiseMoves(const int* labeling, int alpha, double* out) { push_patches(); check(msm_group_pair_moves(ctx, labeling, alpha, out)); }
+    void computePairwiseQueries(int n, const int* q, double* out) { std::lock_guard<std::mutex> lock(lazy); push_patches(); check(msm_group_pair_costs(ctx, n, q, out)); }
+    void computePairwiseMoves(const int* labeling, int alpha, double* out) { std::lock_guard<std::mutex> lock(lazy); push_patches(); check(msm_group_pair_moves(ctx, labeling, alpha, out)); }
+    void computeTripletMovesGroup(const int* labeling, int alpha, float* out) { std::lock_guard<std::mutex> lock(lazy); sync_group(); check(msm_triplet_moves_f32(ctx, labeling, alpha, out)); }
+    // evaluateTotalCostSum (src/DiscreteCostFunction.cpp:41-70) on the device: pairwise data term + triplet term at a labelling
+    double totalCostBatchedGroup(const int* labeling) {
+        std::lock_guard<std::mutex> lock(lazy);
+        push_patches();
+        double sums[3] = {0, 0, 0};
+        check(msm_total_cost(ctx, labeling, sums));
+        return sums[0] + sums[1] + sums[2];
+    }
 
 protected:
     bool is_group() const override { return true; }
@@ -112,6 +122,15 @@ protected:
             check(msm_set_group_patches(ctx, (long long)moff.size() - 1, moff.data(), mkey.data(), mval.data()));
             patches_dirty = false;
         }
+    }
+    void ensure_group_pair_table() {
+        if (pair_epoch == tables_epoch.load()) return;
+        std::lock_guard<std::mutex> lock(lazy);
+        if (pair_epoch == tables_epoch.load()) return;
+        push_patches();
+        pair_table.assign((size_t)m_num_pairs * m_num_labels * m_num_labels, 0.f);
+        if (m_num_pairs > 0 && !moff.empty()) check(msm_group_pair_table(ctx, pair_table.data()));
+        pair_epoch = tables_epoch.load();
     }
     void ensure_triplet_table() {
         if (triplet_epoch == tables_epoch.load()) return;

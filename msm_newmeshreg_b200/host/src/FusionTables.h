@@ -13,6 +13,7 @@
 // path (in an FSL tree next to Fusion.h; here: oracle/_ref builds).  Sweeps, label order, acceptance rule and the returned
 // energy follow Fusion.h:126-243, so for identical tables the labelling is identical (tests/test_gpu_model.py).
 #pragma once
+#include "DiscreteGroupModel.h"
 #include "DiscreteModel.h"
 #include "Fusion/Fusion.h"
 
@@ -158,6 +159,60 @@ public:
                       << ", toQuadratic " << tsec[3] << ", convert + DiscreteModelDummy::initialise " << tsec[4] << ", FastPD ctor " << tsec[5]
                       << ", FastPD::run " << tsec[6] << std::endl;
         return cf->totalCostBatched(labeling);
+    }
+
+    // Groupwise registration (src/group_mesh_registration.cpp:74: Fusion::optimize on a DiscreteGroupModel): no unary term;
+    // per proposal label ONE batched launch for the 4 costs of every inter-subject pair (msm_group_pair_moves) and one for the
+    // 8 costs of every triplet — instead of 4 P + 8 T per-element virtuals.  Sweeps, label order, term order (pairs before
+    // triplets) and the acceptance rule follow include/Fusion/Fusion.h:126-243.
+    static double optimize_group(const std::shared_ptr<DiscreteGroupModel>& energy, bool verbose, int /*numthreads*/ = 1) {
+        auto cf = energy->getGroupCostFunction();
+        const int N = energy->getNumNodes(), L = energy->getNumLabels(), T = energy->getNumTriplets(), P = energy->getNumPairs();
+        const int* pairs = energy->getPairs();
+        const int* triplets = energy->getTriplets();
+        int* labeling = energy->getLabeling();
+        std::vector<double> pmoves((size_t)std::max(P, 1) * 4);
+        std::vector<float> moves((size_t)std::max(T, 1) * 8);
+        auto binary = std::make_shared<FlatBinaryModel>();
+        for (int sweep = 0; sweep < 2; ++sweep)
+            for (int label = 0; label < L; ++label) {
+                bool any = false;
+                for (int node = 0; node < N && !any; ++node) any = labeling[node] != label;
+                if (!any) continue;
+                ELCReduce::PBF<double> pbf;
+                for (int node = 0; node < N; ++node) pbf.AddUnaryTerm(node, 0.0, 0.0);       // base computeUnaryCost returns 0 (src/DiscreteCostFunction.h:34)
+                if (P > 0) {
+                    cf->computePairwiseMoves(labeling, label, pmoves.data());
+                    for (int p = 0; p < P; ++p)
+                        pbf.AddPairwiseTerm(pairs[2 * p], pairs[2 * p + 1], pmoves[4 * (size_t)p], pmoves[4 * (size_t)p + 1], pmoves[4 * (size_t)p + 2],
+                                            pmoves[4 * (size_t)p + 3]);
+                }
+                if (T > 0) {
+                    cf->computeTripletMovesGroup(labeling, label, moves.data());
+                    for (int t = 0; t < T; ++t) {
+                        int ids[3] = {triplets[3 * t], triplets[3 * t + 1], triplets[3 * t + 2]};
+                        double buf[8];
+                        for (int m = 0; m < 8; m++) buf[m] = (double)moves[(size_t)t * 8 + m];
+                        pbf.AddHigherTerm(3, ids, buf);
+                    }
+                }
+                binary->reset();
+                ELCReduce::PBF<double> qpbf;
+                pbf.toQuadratic(qpbf, pbf.maxID() + 1);
+                qpbf.convert(*binary, qpbf.maxID() + 1);
+                pbf.clear();
+                qpbf.clear();
+                binary->initialise();
+                int* take = binary->getLabeling();
+                FPD::FastPD opt(binary, 100);
+                const double newEnergy = opt.run();
+                opt.getLabeling(take);
+                int changed = 0;
+                for (int node = 0; node < N; ++node)
+                    if (labeling[node] != label && take[node] == 1) { labeling[node] = label; changed++; }
+                if (verbose) std::cout << "  LAB " << label << ":\t" << newEnergy << " / " << 100.0 * changed / N << "% CHN" << std::endl;
+            }
+        return cf->totalCostBatchedGroup(labeling);
     }
 };
 

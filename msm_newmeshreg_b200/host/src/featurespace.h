@@ -26,6 +26,7 @@ public:
     // group registration: one data matrix per subject on its own data mesh (src/DiscreteGroupModel.cpp:79)
     void add_subject(const double* data, int V) { subj_.emplace_back(data, data + V); }
     const std::vector<double>& get_data_matrix(int subject) const { return subj_[subject]; }
+    int subjects() const { return (int)subj_.size(); }
 private:
     std::vector<double> in_, ref_;
     std::vector<std::vector<double>> subj_;

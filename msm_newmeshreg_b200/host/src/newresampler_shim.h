@@ -94,7 +94,9 @@ inline NEWMAT::Matrix estimate_rotation_matrix(const Point& p1, const Point& p2)
         for (int j = 0; j < 3; j++) {
             double uu = 0;
             for (int m = 0; m < 3; m++) uu += u[i][m] * u[m][j];
-            R(i + 1, j + 1) += s * u[i][j] + oc * uu;
+            R(i + 1, j + 1) = (R(i + 1, j + 1) + u[i][j] * s) + uu * oc;   // (I + u sin) + u^2 (1 - cos): this association, so that
+                                                                            // displaced control points are bit-identical to the
+                                                                            // oracle's and exact range ties resolve the same way
         }
     return R;
 }

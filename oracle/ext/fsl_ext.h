@@ -473,9 +473,8 @@ inline Point barycentric(const Point& v0, const Point& v1, const Point& v2, cons
 // A6: move every vertex of `up` with the deformation START -> END of a lower-resolution mesh; defined in
 // oracle/ref_cost.cpp over orc::barycentric_mesh_interpolation (oracle/oracle.cpp)
 void barycentric_mesh_interpolation(Mesh& up, const Mesh& START, const Mesh& END, int nthreads = 1);
-// A8: metric_resample(in, ref): per-vertex values of `in` resampled at the vertices of `ref`.  FSL uses an ADAPTIVE
-// barycentric kernel; the stand-in (oracle/ref_cost_ext.cpp) is plain barycentric interpolation, which coincides with it
-// on constant fields — the only case on the path (unit cost-function weights, src/mesh_registration.cpp:330-334).
+// A8: metric_resample(in, ref): per-vertex values of `in` resampled at the vertices of `ref` with FSL's ADAPTIVE
+// barycentric kernel, restated in oracle/geom.h (adaptive_barycentric_weights) from the published algorithm it ports.
 Mesh metric_resample(const Mesh& in, const Mesh& ref, int nthreads = 1);
 // project_mesh is only reached with anatomical meshes (out of scope): loud if called.
 inline Mesh project_mesh(const Mesh&, const Mesh&, const Mesh&, int = 1) { throw MeshException("fsl_ext: project_mesh is not provided"); }

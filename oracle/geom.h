@@ -382,4 +382,96 @@ private:
     std::vector<int> start, items;
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// A8: metric_resample(in, ref) — FSL newresampler's ADAPTIVE BARYCENTRIC resampling ("ADAP_BARY") of per-vertex data
+//     from mesh `in` onto the vertices of mesh `ref`.  Call sites: src/DiscreteGroupModel.cpp:92 (every subject's
+//     patch-wise rotated data mesh -> the template, once per subject and label), src/DiscreteCostFunction.cpp:364-383
+//     (resample_weights: cost-function weights -> control grid), src/featurespace.cc:46, src/group_mesh_registration.cpp:67.
+//     The FSL source is not in the tree; restated from the published algorithm it ports (Connectome Workbench
+//     SurfaceResamplingHelper::computeWeightsAdapBaryArea, "ADAP_BARY_AREA"), with per-vertex areas taken from the two
+//     spheres themselves (one third of the incident triangle areas):
+//       forward[k]  = barycentric weights of ref vertex k in the `in` triangle under it          (3 sources)
+//       reverse[j]  = barycentric weights of in vertex j in the `ref` triangle under it, re-ordered per ref vertex
+//       adapt[k]    = reverse_reorder[k] if it has MORE sources than forward[k], else forward[k]   ("whichever mesh is finer")
+//       w          *= area_ref[k];   corr[j] = sum over k of w(k,j);   w *= area_in[j] / corr[j];   normalise over j.
+//     Sources are visited in ascending vertex order (std::map order), sums accumulate in that order.
+//     A constant field is reproduced exactly (weights sum to 1), which is why unit cost-function weights give
+//     AbsoluteWeights == 1 whatever the details.  No exclusion mask on this path.
+// ---------------------------------------------------------------------------------------------------------
+inline std::vector<double> vertex_areas(const Mesh& M) {
+    std::vector<double> a(M.nvertices(), 0.0);
+    for (int t = 0; t < M.ntriangles(); t++) {
+        const double A = tri_area(M.V[M.F[t][0]], M.V[M.F[t][1]], M.V[M.F[t][2]]) / 3.0;
+        for (int j = 0; j < 3; j++) a[M.F[t][j]] += A;
+    }
+    return a;
+}
+struct ResampleWeights {      // CSR over the vertices of `ref`; sources ascending within a row
+    std::vector<int> off, src;
+    std::vector<double> w;
+};
+// tri/w of every query (closest triangle of M under p, barycentric weights in that triangle's vertex order)
+inline void locate_all(const Mesh& M, const std::vector<Pt>& pts, std::vector<int>& tri, std::vector<double>& w) {
+    SphereLocator loc(M);
+    tri.assign(pts.size(), -1); w.assign(pts.size() * 3, 0.0);
+    for (size_t i = 0; i < pts.size(); i++) {
+        const int t = loc.closest_triangle(pts[i]);
+        tri[i] = t;
+        if (t >= 0) barycentric_weights(M.V[M.F[t][0]], M.V[M.F[t][1]], M.V[M.F[t][2]], pts[i], &w[3 * i]);
+    }
+}
+// The weight assembly, shared by every implementation of A8: inputs are the two sets of point locations.
+inline ResampleWeights adaptive_barycentric_assemble(int Vin, int Vref, const int* in_faces /*[Fin][3]*/, const int* ref_faces /*[Fref][3]*/,
+                                                     const int* fwd_tri, const double* fwd_w /*per ref vertex, in `in`*/, const int* rev_tri,
+                                                     const double* rev_w /*per in vertex, in `ref`*/, const double* area_in, const double* area_ref) {
+    std::vector<std::map<int, double>> adapt(Vref), rr(Vref);
+    for (int j = 0; j < Vin; j++) {
+        if (rev_tri[j] < 0) continue;
+        for (int c = 0; c < 3; c++) rr[ref_faces[3 * rev_tri[j] + c]][j] = rev_w[3 * j + c];
+    }
+    std::vector<double> corr(Vin, 0.0);
+    for (int k = 0; k < Vref; k++) {
+        std::map<int, double> fw;
+        if (fwd_tri[k] >= 0)
+            for (int c = 0; c < 3; c++) fw[in_faces[3 * fwd_tri[k] + c]] = fwd_w[3 * k + c];
+        adapt[k] = rr[k].size() > fw.size() ? rr[k] : fw;
+        for (auto& e : adapt[k]) { e.second *= area_ref[k]; corr[e.first] += e.second; }
+    }
+    ResampleWeights R;
+    R.off.assign(Vref + 1, 0);
+    for (int k = 0; k < Vref; k++) {
+        double sum = 0.0;
+        for (auto& e : adapt[k]) { e.second *= area_in[e.first] / corr[e.first]; sum += e.second; }
+        for (auto& e : adapt[k]) { R.src.push_back(e.first); R.w.push_back(sum != 0.0 ? e.second / sum : e.second); }
+        R.off[k + 1] = (int)R.src.size();
+    }
+    return R;
+}
+inline ResampleWeights adaptive_barycentric_weights(const Mesh& in, const Mesh& ref) {
+    std::vector<int> ft, rt; std::vector<double> fw, rw;
+    locate_all(in, ref.V, ft, fw);
+    if (ref.ntriangles() > 0) locate_all(ref, in.V, rt, rw);
+    else { rt.assign(in.nvertices(), -1); rw.assign((size_t)in.nvertices() * 3, 0.0); }   // `ref` is a bare point set: forward weights only
+    std::vector<int> fi((size_t)in.ntriangles() * 3), fr((size_t)ref.ntriangles() * 3);
+    for (int t = 0; t < in.ntriangles(); t++) for (int j = 0; j < 3; j++) fi[3 * t + j] = in.F[t][j];
+    for (int t = 0; t < ref.ntriangles(); t++) for (int j = 0; j < 3; j++) fr[3 * t + j] = ref.F[t][j];
+    const std::vector<double> ai = vertex_areas(in);
+    const std::vector<double> ar = ref.ntriangles() > 0 ? vertex_areas(ref) : std::vector<double>(ref.nvertices(), 1.0);
+    return adaptive_barycentric_assemble(in.nvertices(), ref.nvertices(), fi.data(), fr.data(), ft.data(), fw.data(), rt.data(), rw.data(), ai.data(),
+                                         ar.data());
+}
+// values[d*Vin + j] -> out[d*Vref + k]
+inline std::vector<double> metric_resample(const Mesh& in, const std::vector<double>& values, int dims, const Mesh& ref) {
+    const ResampleWeights R = adaptive_barycentric_weights(in, ref);
+    const int Vin = in.nvertices(), Vref = ref.nvertices();
+    std::vector<double> out((size_t)dims * Vref, 0.0);
+    for (int d = 0; d < dims; d++)
+        for (int k = 0; k < Vref; k++) {
+            double v = 0.0;
+            for (int e = R.off[k]; e < R.off[k + 1]; e++) v += R.w[e] * values[(size_t)d * Vin + R.src[e]];
+            out[(size_t)d * Vref + k] = v;
+        }
+    return out;
+}
+
 }  // namespace orc

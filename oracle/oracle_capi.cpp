@@ -95,6 +95,15 @@ void orc_locate(const double* xyz, int nv, const int* tris, int nf, const double
     }
 }
 
+// A8: metric_resample (adaptive barycentric), values[d*nv_in + j] -> out[d*nv_ref + k]
+void orc_metric_resample(const double* in_xyz, int nv_in, const int* in_tris, int nf_in, const double* values, int dims, const double* ref_xyz,
+                         int nv_ref, const int* ref_tris, int nf_ref, double* out) {
+    Mesh A = mesh_from(in_xyz, nv_in, in_tris, nf_in), B = mesh_from(ref_xyz, nv_ref, ref_tris, nf_ref);
+    std::vector<double> v(values, values + (size_t)dims * nv_in);
+    const std::vector<double> r = metric_resample(A, v, dims, B);
+    std::copy(r.begin(), r.end(), out);
+}
+
 // ---------------- mesh warp ----------------
 void orc_mesh_interpolate(const double* pts, int m, const double* from_xyz, int nv, const int* tris, int nf, const double* to_xyz, double* out) {
     Mesh M = mesh_from(from_xyz, nv, tris, nf);

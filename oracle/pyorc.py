@@ -126,6 +126,15 @@ def locate(xyz, tris, pts, brute=False, orthogonal=False):
     return tri, w
 
 
+def metric_resample(in_xyz, in_tris, values, ref_xyz, ref_tris):
+    """[EXT] A8 newresampler::metric_resample (adaptive barycentric), restated in oracle/geom.h: values[d][v_in] -> [d][v_ref]."""
+    in_xyz, p1 = _d(in_xyz); in_tris, p2 = _i(in_tris); values = np.atleast_2d(values); values, p3 = _d(values)
+    ref_xyz, p4 = _d(ref_xyz); ref_tris, p5 = _i(ref_tris)
+    out = np.empty((values.shape[0], len(ref_xyz)))
+    lib().orc_metric_resample(p1, len(in_xyz), p2, len(in_tris), p3, values.shape[0], p4, len(ref_xyz), p5, len(ref_tris), out.ctypes.data_as(c_dp))
+    return out
+
+
 def mesh_interpolate(pts, from_xyz, tris, to_xyz):
     """[EXT] barycentric_mesh_interpolation(SPH_up, SPH_low_init, SPH_low_final) restated (src/mesh_registration.cpp:390)."""
     pts, pp = _d(pts); from_xyz, pf = _d(from_xyz); tris, pt = _i(tris); to_xyz, po = _d(to_xyz)

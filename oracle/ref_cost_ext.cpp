@@ -48,28 +48,25 @@ void barycentric_mesh_interpolation(Mesh& up, const Mesh& START, const Mesh& END
     for (int i = 0; i < up.nvertices(); i++) up.set_coord(i, Point(pts[i]));
 }
 
-// A8 stand-in: barycentric interpolation of the per-vertex values (see the declaration for its domain of validity)
+// A8: adaptive barycentric resampling (oracle/geom.h metric_resample): per-vertex values of `in` at the vertices of `ref`
 Mesh metric_resample(const Mesh& in, const Mesh& ref, int) {
     const NEWMAT::Matrix pv = in.get_pvalues();
     const bool column = pv.Ncols() == 1 && pv.Nrows() == in.nvertices();  // set_pvalues(ColumnVector), src/DiscreteCostFunction.cpp:381
     const int dims = column ? 1 : pv.Nrows();
     if (!column && pv.Ncols() != in.nvertices()) throw MeshException("metric_resample: values do not match the mesh");
-    auto val = [&](int d, int v) { return column ? pv(v + 1, 1) : pv(d + 1, v + 1); };
-    Octree tree(in);
-    NEWMAT::Matrix out(column ? ref.nvertices() : dims, column ? 1 : ref.nvertices());
-    for (int i = 0; i < ref.nvertices(); i++) {
-        const Point p = ref.get_coord(i);
-        const Triangle T = tree.get_closest_triangle(p);
-        double w[3];
-        orc::barycentric_weights(T.get_vertex_coord(0), T.get_vertex_coord(1), T.get_vertex_coord(2), p, w);
-        for (int d = 0; d < dims; d++) {
-            const double v = w[0] * val(d, T.get_vertex_no(0)) + w[1] * val(d, T.get_vertex_no(1)) + w[2] * val(d, T.get_vertex_no(2));
-            if (column) out(i + 1, 1) = v; else out(d + 1, i + 1) = v;
+    const int Vin = in.nvertices(), Vref = ref.nvertices();
+    std::vector<double> vals((size_t)dims * Vin);
+    for (int d = 0; d < dims; d++)
+        for (int v = 0; v < Vin; v++) vals[(size_t)d * Vin + v] = column ? pv(v + 1, 1) : pv(d + 1, v + 1);
+    const std::vector<double> res = orc::metric_resample(in.synced(), vals, dims, ref.synced());
+    NEWMAT::Matrix out(column ? Vref : dims, column ? 1 : Vref);
+    for (int d = 0; d < dims; d++)
+        for (int i = 0; i < Vref; i++) {
+            if (column) out(i + 1, 1) = res[i]; else out(d + 1, i + 1) = res[(size_t)d * Vref + i];
         }
-    }
-    Mesh res = ref;
-    res.set_pvalues(out);
-    return res;
+    Mesh o = ref;
+    o.set_pvalues(out);
+    return o;
 }
 
 }  // namespace newresampler
