@@ -78,6 +78,8 @@ int msm_reset_source(msm_ctx* ctx, const double* xyz);
  * abs_weights = AbsoluteWeights per CP (resample_weights :364-383, [EXT] metric_resample); NULL = all 1. */
 int msm_set_cpgrid(msm_ctx* ctx, const double* xyz, int N, const int* tris, int T, const double* maxsep,
                    const double* orig_xyz, const double* abs_weights);
+/* AbsoluteWeights alone (resample_weights runs in every get_source_data, src/DiscreteCostFunction.cpp:364-383,409,480): double[N]. */
+int msm_set_abs_weights(msm_ctx* ctx, const double* abs_weights);
 /* reset_CPgrid (src/DiscreteCostFunction.h:182) */
 int msm_reset_cpgrid(msm_ctx* ctx, const double* xyz);
 /* Multi-GPU: this context evaluates unary rows / patches only for CPs [k_begin,k_end). */

@@ -24,7 +24,7 @@ class MsmParams(C.Structure):
 
 EXPORTS = [
     "msm_default_params", "msm_create", "msm_destroy", "msm_last_error", "msm_set_stream", "msm_synchronize", "msm_set_params",
-    "msm_set_target", "msm_set_source", "msm_reset_source", "msm_set_cpgrid", "msm_reset_cpgrid", "msm_set_shard", "msm_set_labels",
+    "msm_set_target", "msm_set_source", "msm_reset_source", "msm_set_cpgrid", "msm_set_abs_weights", "msm_reset_cpgrid", "msm_set_shard", "msm_set_labels",
     "msm_set_pairs", "msm_set_triplets", "msm_set_group", "msm_build_patches", "msm_patch_count", "msm_get_patches",
     "msm_unary_table", "msm_unary_table_dev", "msm_triplet_costs", "msm_triplet_table", "msm_triplet_table_dev", "msm_triplet_moves",
     "msm_triplet_moves_f32", "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count", "msm_patch_build_stats",
@@ -153,6 +153,10 @@ class Context:
             abs_weights, pa = _d(abs_weights)
         self._ck(lib().msm_set_cpgrid(self._h, px, len(xyz), pt, len(tris), pm, po, pa))
         self.N = len(xyz); self.k_begin, self.k_end = 0, self.N
+
+    def set_abs_weights(self, aw):
+        aw, pa = _d(aw); assert len(aw) == self.N
+        self._ck(lib().msm_set_abs_weights(self._h, pa))
 
     def reset_cpgrid(self, xyz):
         xyz, px = _d(xyz); assert len(xyz) == self.N

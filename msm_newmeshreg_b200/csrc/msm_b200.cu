@@ -565,6 +565,14 @@ int msm_set_cpgrid(msm_ctx* ctx, const double* xyz, int N, const int* tris, int 
     return 0;
 }
 
+int msm_set_abs_weights(msm_ctx* ctx, const double* abs_weights) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->N <= 0) FAIL("msm_set_cpgrid must be called first");
+    if (upload_as_float(ctx, ctx->d_absw, abs_weights, (size_t)ctx->N)) return 1;
+    ctx->have_unary = false;
+    return 0;
+}
+
 int msm_reset_cpgrid(msm_ctx* ctx, const double* xyz) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->N <= 0) FAIL("msm_set_cpgrid must be called first");

@@ -143,6 +143,11 @@ class Model:
     def reset_cpgrid(self, cxyz):
         cxyz, p = _d(cxyz); self._ck(self._L.msmhost_model_reset_cpgrid(self.h, p))
 
+    def set_weights(self, w):
+        """cost-function weighting (setupCostFunctionWeighting, src/mesh_registration.cpp:323-334): w[rows][source vertices]."""
+        w = np.atleast_2d(w); w, p = _d(w)
+        self._ck(self._L.msmhost_model_set_weights(self.h, p, w.shape[0], w.shape[1]))
+
     def setup(self):
         self._ck(self._L.msmhost_model_setup(self.h)); self._sizes()
 

@@ -109,6 +109,7 @@ struct ModelBox {
     std::shared_ptr<ModelT> model;
     myparam params;
     newresampler::Mesh target, source;
+    NEWMAT::Matrix cfweight;   // optional cost-function weighting (rows x source vertices); empty = the driver's unit weights
 };
 template <typename F>
 int guard(F&& f) {
@@ -229,9 +230,22 @@ int msmhost_model_reset_cpgrid(void* h, const double* cxyz) {  // :393
         b->model->reset_CPgrid(g);
     });
 }
+// cost-function weighting handed to setupCostFunctionWeighting (src/mesh_registration.cpp:323-334): w[rows][source vertices]
+int msmhost_model_set_weights(void* h, const double* w, int rows, int V) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        b->cfweight.ReSize(rows, V);
+        for (int r = 0; r < rows; r++) for (int v = 0; v < V; v++) b->cfweight(r + 1, v + 1) = w[(size_t)r * V + v];
+    });
+}
 int msmhost_model_setup(void* h) {  // :330-337
     auto* b = (ModelBox*)h;
     return guard([&] {
+        if (b->cfweight.Ncols() > 0) {
+            b->model->setupCostFunctionWeighting(b->cfweight);
+            b->model->setupCostFunction();
+            return;
+        }
 #ifdef WITH_REF_COST
         // the driver hands the cost function unit weights when no weighting is supplied (:330-334); the reference's
         // own initialize() would otherwise ReSize them to zeros (src/DiscreteCostFunction.cpp:115-116).  The product

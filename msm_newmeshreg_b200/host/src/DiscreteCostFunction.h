@@ -16,10 +16,12 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <mutex>
 
 #include "../../../include/msm_b200.h"
 #include "featurespace.h"
+#include "mesh_warp.h"
 
 #define RAD 100.0
 #define EPSILON 1.0E-8
@@ -177,8 +179,34 @@ public:
     void set_dataaffintyweighting(const NEWMAT::Matrix& HRWeight) { _HIGHREScfweight = HRWeight; source_dirty = true; }
 
     //---GET DATA---//
+    // resample_weights (:364-383): AbsoluteWeights = metric_resample (adaptive barycentric, [EXT] A8) of the per-vertex maximum
+    // over the weight rows, from the current source mesh onto the current control grid.  Unit weights (the driver's default,
+    // src/mesh_registration.cpp:330-334) resample to exactly 1 whatever the kernel: skipped.
+    void resample_weights() {
+        if (!abs_weights_given) {
+            bool unit = true;
+            const int V = _SOURCE.nvertices(), R = _HIGHREScfweight.Ncols() == V ? _HIGHREScfweight.Nrows() : 0;
+            for (int j = 1; j <= R && unit; j++)
+                for (int k = 1; k <= V; k++) if (_HIGHREScfweight(j, k) != 1.0) { unit = false; break; }
+            if (unit) {
+                if (!abs_weights.empty()) { abs_weights.assign(_CPgrid.nvertices(), 1.0); check(msm_set_abs_weights(ctx, abs_weights.data())); abs_weights.clear(); }
+                return;
+            }
+            std::vector<double> mx(V);
+            for (int k = 1; k <= V; k++) {
+                double m = std::numeric_limits<double>::lowest();
+                for (int j = 1; j <= R; j++) if (_HIGHREScfweight(j, k) > m) m = _HIGHREScfweight(j, k);
+                mx[k - 1] = m;
+            }
+            abs_weights = newresampler::metric_resample(_SOURCE, mx.data(), 1, _CPgrid);
+            check(msm_set_abs_weights(ctx, abs_weights.data()));
+        }
+    }
+    const std::vector<double>& absolute_weights() const { return abs_weights; }
+
     virtual void get_source_data() {  // :394-410 / :458-481 : patches, then the whole unary table in one launch
         { HostTimer t("    sync_device_state"); sync_device_state(); }
+        { HostTimer t("    resample_weights"); resample_weights(); }
         { HostTimer t("    msm_build_patches"); check(msm_build_patches(ctx)); }
         unary_pristine.resize((size_t)m_num_labels * m_num_nodes);   // every entry is written by msm_unary_table
         { HostTimer t("    msm_unary_table"); check(msm_unary_table(ctx, unary_pristine.data())); }
@@ -219,7 +247,7 @@ public:
     }
     // AbsoluteWeights (resample_weights, :364-383): identically 1 for unit weights; otherwise supplied by the caller
     // because the reference obtains them from FSL's metric_resample ([EXT] A8).
-    void set_absolute_weights(const std::vector<double>& aw) { abs_weights = aw; grid_dirty = true; }
+    void set_absolute_weights(const std::vector<double>& aw) { abs_weights = aw; abs_weights_given = true; grid_dirty = true; }
 
     //---REPORT AND DEBUG---//
     void report() {}
@@ -343,6 +371,7 @@ protected:
     NEWMAT::Matrix _HIGHREScfweight;
     NEWMAT::ColumnVector MAXSEP;
     std::vector<double> abs_weights;
+    bool abs_weights_given = false;   // set_absolute_weights: explicit values instead of resample_weights()
     std::shared_ptr<featurespace> FEAT;
     std::vector<newresampler::Point> _labels;
     std::string dopt;

@@ -2,6 +2,8 @@
 // (oracle/_ref/libref_cost.so, tests/test_reference_pin.py).
 #include "oracle.h"
 
+#include <limits>
+
 #include <omp.h>
 
 #include <cstring>
@@ -322,9 +324,20 @@ void CostFunction::get_source_data() {  // :394-410 (uni) / :458-481 (multi): sa
     for (int k = 0; k < CPgrid.nvertices(); k++)
         for (int i = 0; i < SOURCE.nvertices(); i++)
             if (within_controlpt_range(k, i)) sourceinrange[k].push_back(i);
-    // resample_weights() (:364-383) = metric_resample of max-over-channel weights onto the CP grid [EXT A8];
-    // identically 1 for unit weights.  Kept as an input (default ones).
-    if ((int)AbsoluteWeights.size() != CPgrid.nvertices()) AbsoluteWeights.assign(CPgrid.nvertices(), 1.0);
+    // resample_weights() (:364-383): maximum over the weight rows per source vertex, metric_resample'd ([EXT] A8, geom.h)
+    // from the CURRENT source mesh onto the CURRENT control grid.  Explicitly supplied AbsoluteWeights win (tests).
+    if (!absweights_given) {
+        if (cfweight.empty()) AbsoluteWeights.assign(CPgrid.nvertices(), 1.0);   // the reference never runs without weights; unit weights -> 1
+        else {
+            std::vector<double> mx(SOURCE.nvertices());
+            for (int i = 0; i < SOURCE.nvertices(); i++) {
+                double m = std::numeric_limits<double>::lowest();
+                for (const auto& row : cfweight) if (row[i] > m) m = row[i];
+                mx[i] = m;
+            }
+            AbsoluteWeights = metric_resample(SOURCE, mx, 1, CPgrid);
+        }
+    }
 }
 
 static inline double weight_of(const std::vector<std::vector<double>>& cfw, int d, int i) {

@@ -81,6 +81,7 @@ public:
     std::vector<std::vector<double>> input;     // FEAT->get_input_val(d+1, v+1) [C][Vs]
     std::vector<std::vector<double>> cfweight;  // _HIGHREScfweight rows (0, 1 or C rows)
     std::vector<double> MAXSEP, AbsoluteWeights;
+    bool absweights_given = false;   // set_absweights: explicit values instead of resample_weights()
     double MVDmax = 0, MEANANGLE = 0;
     std::vector<Pt> labels;
     std::vector<Mat3> ROT;

@@ -139,7 +139,8 @@ void orc_cf_set_params(void* h, double lambda, double rexp, double mu, double ka
 void orc_cf_set_meshes(void* h, const double* txyz, int Vt, const int* ttris, int Ft, const double* sxyz, int Vs,
                        const double* cxyz, int N, const int* ctris, int T) {
     CostFunction* cf = (CostFunction*)h;
-    Mesh tgt = mesh_from(txyz, Vt, ttris, Ft), src = mesh_from(sxyz, Vs, nullptr, 0), cp = mesh_from(cxyz, N, ctris, T);
+    // the source is the template icosphere deformed (SPH_orig warped, src/mesh_registration.cpp:66,336): same topology
+    Mesh tgt = mesh_from(txyz, Vt, ttris, Ft), src = mesh_from(sxyz, Vs, Vs == Vt ? ttris : nullptr, Vs == Vt ? Ft : 0), cp = mesh_from(cxyz, N, ctris, T);
     cf->set_meshes(tgt, src, cp);
     cf->set_initial_angles();
 }
@@ -159,7 +160,8 @@ void orc_cf_set_cfweight(void* h, int rows, const double* w, int Vs) {
     cf->cfweight.assign(rows, {});
     for (int d = 0; d < rows; d++) cf->cfweight[d].assign(w + (size_t)d * Vs, w + (size_t)(d + 1) * Vs);
 }
-void orc_cf_set_absweights(void* h, const double* aw, int n) { ((CostFunction*)h)->AbsoluteWeights.assign(aw, aw + n); }
+void orc_cf_set_absweights(void* h, const double* aw, int n) { ((CostFunction*)h)->AbsoluteWeights.assign(aw, aw + n); ((CostFunction*)h)->absweights_given = true; }
+void orc_cf_get_absweights(void* h, double* out) { CostFunction* cf = (CostFunction*)h; std::copy(cf->AbsoluteWeights.begin(), cf->AbsoluteWeights.end(), out); }
 void orc_cf_set_spacings(void* h, const double* maxsep, int n, double MVDmax) {
     CostFunction* cf = (CostFunction*)h;
     cf->MAXSEP.assign(maxsep, maxsep + n); cf->MVDmax = MVDmax;

@@ -194,6 +194,10 @@ class CostFunction:
     def set_absweights(self, aw):
         aw, p = _d(aw); lib().orc_cf_set_absweights(self.h, p, len(aw))
 
+    def absweights(self):
+        """AbsoluteWeights after get_source_data (resample_weights, src/DiscreteCostFunction.cpp:364-383)."""
+        out = np.empty(self.N); lib().orc_cf_get_absweights(self.h, out.ctypes.data_as(c_dp)); return out
+
     def set_spacings(self, maxsep, mvdmax):
         maxsep, p = _d(maxsep); lib().orc_cf_set_spacings(self.h, p, len(maxsep), C.c_double(mvdmax))
 

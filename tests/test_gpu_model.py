@@ -228,3 +228,29 @@ def test_table_aware_fusion_driver_equals_fusion_optimize(built, C):
     assert np.array_equal(labs[0], labs[1]), f"{(labs[0] != labs[1]).sum()} of {P.N} labels differ"
     assert abs(ens[0] - ens[1]) <= 1e-6 * abs(ens[0])
     assert len(np.unique(labs[0])) > 1
+
+
+@pytest.mark.skipif(not _have_refcost(), reason="oracle/_ref/libref_cost.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("C", [1, 4])
+def test_non_unit_costfunction_weights_give_the_reference_absolute_weights(built, C):
+    """resample_weights (src/DiscreteCostFunction.cpp:364-383): with a non-constant cost-function weighting the per-control-
+    point AbsoluteWeights are the adaptive-barycentric resampling ([EXT] A8) of the per-vertex maximum weight — computed by
+    the product (GPU point location + host weight assembly), not taken as an input.  The whole unary table against the
+    reference's own classes."""
+    P = pb.make_problem(4, 2, C, seed=23, warp=0.3, deform_cp=0.1)
+    rows = 1 if C == 1 else C
+    w = 0.25 + np.abs(np.stack([pb.random_field(P.sxyz, 900 + r) for r in range(rows)]))
+    tabs = []
+    for lib in (None, "ref"):
+        m = _model(P) if lib is None else _ref_model(P)
+        m.reset_meshspace(P.sxyz); m.reset_cpgrid(P.cxyz)
+        m.set_weights(w)
+        m.setup()
+        tabs.append(m.unary()); m.close()
+    good = np.ones(P.N, bool); good[pb.singular_nodes(P)] = False
+    e = pb.rel_err(tabs[0][:, good], tabs[1][:, good], 1e-2)
+    assert e.max() < 1e-5, float(e.max())
+    # and the weights do matter: the same table with unit weights is different
+    m = _model(P); m.reset_meshspace(P.sxyz); m.reset_cpgrid(P.cxyz); m.setup()
+    assert np.abs(m.unary() - tabs[0]).max() > 1e-2
+    m.close()

@@ -272,3 +272,32 @@ def test_total_energy_is_sum_of_terms():
     q = np.array([[t, lab[P.triplets[t, 0]], lab[P.triplets[t, 1]], lab[P.triplets[t, 2]]] for t in range(P.T)], np.int32)
     expect = U[lab, np.arange(P.N)].sum() + cf.triplet_costs(q).sum()
     assert abs(cf.total(lab) - expect) < 1e-9 * abs(expect)                          # :41-70
+
+
+# ------------------------------------------------------------------------------------------------ [EXT] A8 metric_resample
+def test_adaptive_barycentric_resampling_known_answers():
+    """oracle/geom.h metric_resample (adaptive barycentric, restated from the published ADAP_BARY_AREA algorithm):
+    a mesh resampled onto itself is the identity; constants are reproduced exactly on any pair of meshes; a smooth field
+    survives a small warp; going from a FINE to a COARSE sphere every coarse vertex gathers many sources (the reverse sets
+    win), from coarse to fine exactly the 3 corners of the enclosing triangle (the forward sets win)."""
+    x5, t5 = pyorc.icosphere(5)
+    x3, t3 = pyorc.icosphere(3)
+    f = pb.random_field(x5, 5)
+    assert np.abs(pyorc.metric_resample(x5, t5, f, x5, t5)[0] - f).max() < 1e-12
+    w5 = pb.smooth_warp(x5, 9, 1.0)
+    for (a, ta, b, tb) in ((w5, t5, x5, t5), (x5, t5, x3, t3), (x3, t3, x5, t5)):
+        c = pyorc.metric_resample(a, ta, np.full(len(a), 3.25), b, tb)[0]
+        assert np.abs(c - 3.25).max() < 1e-12
+    g = pyorc.metric_resample(w5, t5, f, x5, t5)[0]
+    assert np.abs(g - f).max() < 0.15 and np.corrcoef(g, f)[0, 1] > 0.995
+    # fine -> coarse: an impulse at one fine vertex reaches at most the 3 coarse corners around it, and every coarse vertex
+    # averages over a whole neighbourhood (smoother than point sampling)
+    down = pyorc.metric_resample(x5, t5, f, x3, t3)[0]
+    point = f[:len(x3)]                                   # nested numbering: coarse vertices are the first fine vertices
+    assert np.abs(down - point).max() > 1e-3              # not plain barycentric interpolation (which would return `point` exactly)
+    imp = np.zeros(len(x5)); imp[4000] = 1.0
+    hit = np.nonzero(pyorc.metric_resample(x5, t5, imp, x3, t3)[0])[0]
+    assert 1 <= len(hit) <= 3
+    # coarse -> fine: forward sets — at the coarse vertices themselves the value is the coarse value
+    up = pyorc.metric_resample(x3, t3, point, x5, t5)[0]
+    assert np.abs(up[:len(x3)] - point).max() < 1e-9

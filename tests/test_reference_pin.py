@@ -255,3 +255,22 @@ def test_bench_reference_sample_equals_oracle_sample():
     q = np.array([[t, a if c & 4 else lab[trip[t, 0]], a if c & 2 else lab[trip[t, 1]], a if c & 1 else lab[trip[t, 2]]]
                   for a in range(L) for t in range(nt) for c in range(8)], np.int32)
     assert pb.rel_err(tabs["moves"].ravel(), cf.triplet_costs(q), 1e-9).max() < 1e-9
+
+
+@pytest.mark.parametrize("C", [1, 3])
+def test_resample_weights_oracle_equals_reference_build(C):
+    """Non-unit cost-function weighting: AbsoluteWeights = metric_resample([EXT] A8) of the per-vertex maximum weight
+    (src/DiscreteCostFunction.cpp:364-383) multiplies every unary cost.  The oracle port's restatement against the
+    reference's own get_source_data / computeUnaryCosts."""
+    P = pb.make_problem(4, 2, C, seed=31, warp=0.3, deform_cp=0.1)
+    rows = 1 if C == 1 else C
+    w = 0.25 + np.abs(np.stack([pb.random_field(P.sxyz, 700 + r) for r in range(rows)]))
+    m = pyrefcost.model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=C > 1, threads=1, **pb.DEFAULT_PARAMS)
+    m.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref); m.initialize()
+    m.reset_meshspace(P.sxyz); m.reset_cpgrid(P.cxyz); m.set_weights(w); m.setup()
+    cf = pb.oracle_costfunction(P, cfweight=w); cf.get_source_data()
+    aw = cf.absweights()
+    assert aw.std() > 1e-2 and aw.min() > 0.2                     # really resampled, not the unit default
+    good = np.ones(P.N, bool); good[pb.singular_nodes(P)] = False
+    assert np.abs(cf.unary_costs()[:, good] - m.unary()[:, good]).max() < 1e-12
+    m.close()
