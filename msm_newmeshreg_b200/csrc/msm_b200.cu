@@ -134,7 +134,7 @@ struct msm_ctx {
     int pack_cp = 0;
     bool patches_padded = false;   // packed streams are fixed-capacity rows [Ns][pad_cap] (one-pass build, patchfast.cuh), not CSR
     int pad_cap = 0;
-    DevBuf d_pflags;
+    DevBuf d_pflags, d_end;
     long long fast_builds = 0, exact_builds = 0;
 
     DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
@@ -727,7 +727,9 @@ int msm_build_patches(msm_ctx* ctx) {
             f.vkey = ctx->d_vkey.as<int>();
             f.Cp = Cp; f.C = ctx->Cs; f.wrows = ctx->wrows; f.univariate = ctx->multivariate ? 0 : 1;
             f.feat = ctx->d_sfeat.as<double>(); f.wgt = ctx->d_swgt.as<float>();
+            CK(ctx->d_end.ensure((size_t)Ns * 4));
             f.counts = ctx->d_counts.as<int>(); f.idx = ctx->d_idx.as<int>();
+            f.off = ctx->d_off.as<int>(); f.end = ctx->d_end.as<int>();
             f.px = ctx->d_px.as<float>(); f.py = ctx->d_py.as<float>(); f.pz = ctx->d_pz.as<float>();
             f.pa = ctx->d_pa.as<float>(); f.pw = ctx->d_pw.as<float>();
             f.flags = ctx->d_pflags.as<int>();
@@ -972,7 +974,7 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
     UnaryArgs a;
     a.k_begin = ctx->k_begin; a.Ns = Ns; a.L = L; a.Lg = Lg; a.G = (L + Lg - 1) / Lg;
     a.off = ctx->d_off.as<int>();
-    a.cnt = ctx->patches_padded ? ctx->d_counts.as<int>() : nullptr; a.cap = ctx->pad_cap;
+    a.end = ctx->patches_padded ? ctx->d_end.as<int>() : ctx->d_off.as<int>() + 1;
     a.px = ctx->d_px.as<float>(); a.py = ctx->d_py.as<float>(); a.pz = ctx->d_pz.as<float>();
     a.pa = ctx->d_pa.as<float>(); a.pw = ctx->d_pw.as<float>();
     a.total = ctx->patches_padded ? Ns * ctx->pad_cap : (int)ctx->total;
@@ -997,7 +999,7 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
     Timer tm(ctx, "unary");
     {
         UnarySetupArgs s;
-        s.k_begin = ctx->k_begin; s.L = L; s.off = a.off; s.cnt = a.cnt; s.cap = a.cap; s.px = a.px; s.py = a.py; s.pz = a.pz;
+        s.k_begin = ctx->k_begin; s.L = L; s.off = a.off; s.end = a.end; s.px = a.px; s.py = a.py; s.pz = a.pz;
         s.Kd = ctx->d_Kd.as<double>(); s.cp = ctx->d_cp.as<double>(); s.ico = a.ico; s.hint = a.hint;
         s.hint_face = ctx->d_hint_face.as<int>(); s.lab12 = ctx->d_lab12.as<float>();
         s.tref = ctx->d_tref.as<float>();

@@ -27,6 +27,7 @@ struct PatchFastArgs {
     const double* feat;                      // [C][V]
     const float* wgt;                        // [wrows][V]
     int* counts;                             // [Ns]
+    int* off; int* end;                      // [Ns] row r of the packed streams: [r cap, r cap + count)
     int* idx;                                // [Ns][cap] member ids, packed order
     float* px; float* py; float* pz;         // [Ns][cap]
     float* pa; float* pw;                    // [Cp][Ns][cap]
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(kPatchWarps * 32) k_patch_fused(PatchFastArgs 
         atomicMax(a.flags + 2, n);
         atomicAdd(a.flags + 3, min(n, a.cap));
         a.counts[row] = min(n, a.cap);
+        a.off[row] = row * a.cap; a.end[row] = row * a.cap + min(n, a.cap);
     }
     n = min(n, a.cap);
     __syncwarp();

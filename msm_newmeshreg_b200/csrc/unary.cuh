@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(128) k_vertex_key(int V, const double* __restr
 
 struct UnarySetupArgs {
     int k_begin, L;
-    const int* off;                     // [Ns+1] CSR offsets of the packed streams, or (cnt != nullptr) unused:
-    const int* cnt; int cap;            // fixed-capacity rows [Ns][cap] with cnt[row] samples each (patchfast.cuh)
+    const int* off; const int* end;     // samples of row r: [off[r], end[r]) of the packed streams (CSR: end = off + 1; fixed-capacity
+                                        // rows of the one-pass build, patchfast.cuh: off[r] = r cap, end[r] = off[r] + count)
     const float* px; const float* py; const float* pz;  // packed offsets r
     const double* Kd;                   // [N][L][9]  R_kl - I
     const double* cp;                   // [N][3]
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
 #pragma unroll
     for (int j = 0; j < 9; j++) A[j] = a.hint.hdual[(size_t)f * 9 + j];
     const double x0 = A[0] * ox + A[1] * oy + A[2] * oz, x1 = A[3] * ox + A[4] * oy + A[5] * oz, x2 = A[6] * ox + A[7] * oy + A[8] * oz;
-    const int sb = a.cnt ? row * a.cap : a.off[row], se = a.cnt ? sb + a.cnt[row] : a.off[row + 1];
+    const int sb = a.off[row], se = a.end[row];
     for (int s = sb + lane; s < se; s += 32) {
         const double x = a.px[s], y = a.py[s], z = a.pz[s];
         a.pcx[s] = (float)(x0 + (A[0] * x + A[1] * y + A[2] * z));
@@ -131,8 +131,7 @@ __global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
 
 struct UnaryArgs {
     int k_begin, Ns, L, G, Lg;          // shard rows, labels, label groups, labels per group
-    const int* off;                     // [Ns+1] CSR offsets, or (cnt != nullptr) fixed-capacity rows:
-    const int* cnt; int cap;            // [Ns][cap], cnt[row] samples each (patchfast.cuh)
+    const int* off; const int* end;     // samples of row r: [off[r], end[r]) (see UnarySetupArgs)
     const float* px; const float* py; const float* pz;     // packed offsets r = SRC - CP_k
     const float* pcx; const float* pcy; const float* pcz;  // corner coordinates c
     const float* pa; const float* pw;   // packed source features / weights [Cp][total]
@@ -250,7 +249,7 @@ __device__ __forceinline__ void unary_body(const UnaryArgs& a) {
     const int row = blockIdx.x / a.G, g = blockIdx.x - row * a.G;
     const int k = a.k_begin + row;
     const int l0 = g * a.Lg, l1 = min(a.L, l0 + a.Lg), nl = l1 - l0;
-    const int s0 = a.cnt ? row * a.cap : a.off[row], P = a.cnt ? a.cnt[row] : a.off[row + 1] - s0;
+    const int s0 = a.off[row], P = a.end[row] - s0;
     const int tid = threadIdx.x;
     // smem carve (16-byte aligned pieces first): lab[Lg][12] | rc4[P] = (rx,ry,rz,cx) | c2[P] = (cy,cz) | a[CP_][P] |
     // w[CP_][P] | tbuf[Lg][P]
