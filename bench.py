@@ -528,12 +528,86 @@ def bench_group(args, rank, world, local, metric, unit, emit=True):
                        "S": S, "N": N, "T": T, "L": L, "table_bytes": 4 * evals, "checksum": checksum},
             "gpu_launches": int(ctx.launch_count() - launches0)})
     ctx.close()
+    if args.group_data_term:
+        try:
+            dt = group_data_term(args, rank, world, local)
+        except Exception as e:
+            dt = {"error": f"{type(e).__name__}: {e}"}
+        if line is not None:
+            line["data_term"] = dt
     if emit:
         if rank == 0:
             emit_line(json.dumps(line))
         if world > 1:
             dist.barrier(); dist.destroy_process_group()
     return line
+
+
+def group_data_term(args, rank, world, local):
+    """The groupwise DATA term (src/DiscreteGroupCostFunction.cpp:32-54 and its producers, src/DiscreteGroupModel.cpp:72-117)
+    through the product's DiscreteGroupModel, subjects sharded over the GPUs: every rank produces the patch-wise rotated and
+    resampled data of ITS subjects (S L adaptive-barycentric resamplings: GPU range queries + GPU point location), ONE
+    all-gather of the [S][L][V_template] values (NCCL), then every rank assembles the patch maps and evaluates the 4
+    fusion-move costs of every inter-subject pair for its share of the proposal labels."""
+    import torch
+    import torch.distributed as dist
+    from msm_newmeshreg_b200 import host, sharding
+    S, cpl, dl = args.group_subjects, args.group_cp_level, args.group_data_level
+    txyz, ttris = host.icosphere(dl)
+    cxyz0, ctris = host.icosphere(cpl)
+    mvd = float(np.linalg.norm(cxyz0[ctris[:, 0]] - cxyz0[ctris[:, 1]], axis=1).mean())
+    shared = random_field(txyz, 299)
+    data = np.stack([random_field(txyz, 300 + s) + 0.5 * shared for s in range(S)])
+    m = host.GroupModel(lam=f32(0.2), sgres=cpl + 2, cpres=cpl, threads=max(1, (os.cpu_count() or 1) // world))
+    m.set_data(txyz, ttris, data)
+    t0 = time.perf_counter()
+    m.initialize()
+    for s in range(S):
+        m.reset_meshspace(s, smooth_warp(txyz, 400 + s, 0.15 * mvd))
+        m.reset_cpgrid(s, smooth_warp(cxyz0, 450 + s, 0.05 * mvd))
+    s0, s1 = sharding.shard_range(S, rank, world)
+    m.set_subject_shard(s0, s1)
+    t1 = time.perf_counter()
+    m.setup()                                            # cliques + this rank's S_local * L resamplings
+    t2 = time.perf_counter()
+    if world > 1:
+        mine = torch.from_numpy(np.stack([m.rotated_all(s) for s in range(s0, s1)])).cuda()
+        per = (S + world - 1) // world
+        pad = torch.zeros((per, m.L, m.Vt), dtype=torch.float64, device="cuda")
+        pad[:s1 - s0] = mine
+        allv = torch.empty((world * per, m.L, m.Vt), dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allv, pad)
+        allv = allv.cpu().numpy()
+        for r in range(world):
+            a, b = sharding.shard_range(S, r, world)
+            if r != rank:
+                for s in range(a, b):
+                    m.set_rotated(s, allv[r * per + (s - a)])
+    t3 = time.perf_counter()
+    if world > 1:
+        m.finish_setup()                                 # patch maps of every subject -> CSR -> device
+    lab = np.random.default_rng(7).integers(0, m.L, m.N).astype(np.int32)
+    m.pair_moves(lab, 0)                                 # first call uploads the maps
+    t4 = time.perf_counter()
+    mine_labels = [a_ for a_ in range(m.L) if a_ % world == rank]
+    chk = 0.0
+    for a_ in mine_labels:
+        chk += float(m.pair_moves(lab, a_).sum())
+    t5 = time.perf_counter()
+    tt = torch.tensor([t2 - t1, t3 - t2, t4 - t3, t5 - t4, chk], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        tt = torch.cat([mx[:4], sm[4:]])
+    tt = tt.cpu().numpy()
+    out = {"S": S, "data_mesh": f"ico{dl}", "control_grid": f"ico{cpl}", "nodes": m.N, "pairs": m.P, "L": m.L,
+           "producers_s": float(tt[0]), "exchange_s": float(tt[1]), "patch_maps_and_upload_s": float(tt[2]),
+           "pair_moves_all_labels_s": float(tt[3]), "pair_move_evals": int(m.P) * 4 * int(m.L),
+           "pair_move_evals_per_s": int(m.P) * 4 * int(m.L) / float(tt[3]), "checksum": float(tt[4]),
+           "exchanged_bytes": int(S) * int(m.L) * int(m.Vt) * 8 if world > 1 else 0,
+           "note": "wall clock, max over ranks; producers = S L adaptive-barycentric resamplings sharded by subject"}
+    m.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -560,6 +634,10 @@ def main():
     ap.add_argument("--secondary", type=int, default=1,
                     help="1: after the headline measurement also run the CP-sharded (configs[2] as written) and groupwise (configs[4]) "
                          "steps on the same GPUs and attach them as `secondary`; 0: skip")
+    ap.add_argument("--group-data-term", type=int, default=0,
+                    help="--mode group: also run the groupwise DATA term (producers sharded by subject + all-gather + pair moves); "
+                         "tens of seconds at the default size")
+    ap.add_argument("--group-data-level", type=int, default=6)
     ap.add_argument("--group-subjects", type=int, default=16)
     ap.add_argument("--group-cp-level", type=int, default=4)
     ap.add_argument("--cp-exchange", default="mc", choices=["mc", "p2p", "nccl"],

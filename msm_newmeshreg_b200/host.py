@@ -292,6 +292,26 @@ class GroupModel:
         self._ck(self._L.msmhost_group_rotated(self.h, int(subject), int(label), out.ctypes.data_as(c_dp)))
         return out
 
+    def pair_moves(self, labeling, alpha):
+        """The 4 fusion-move costs of every inter-subject pair for proposal label alpha: [P][4] (one GPU launch)."""
+        labeling, p = _i(labeling); out = np.empty((self.P, 4))
+        self._ck(self._L.msmhost_group_pair_moves(self.h, p, int(alpha), out.ctypes.data_as(c_dp)))
+        return out
+
+    # multi-GPU: subjects [s0, s1) are produced by this rank; exchange rotated_all / set_rotated, then finish_setup
+    def set_subject_shard(self, s0, s1):
+        self._ck(self._L.msmhost_group_set_subject_shard(self.h, int(s0), int(s1)))
+
+    def rotated_all(self, subject):
+        out = np.empty((self.L, self.Vt)); self._ck(self._L.msmhost_group_rotated_all(self.h, int(subject), out.ctypes.data_as(c_dp))); return out
+
+    def set_rotated(self, subject, values):
+        values, p = _d(values); assert values.shape == (self.L, self.Vt)
+        self._ck(self._L.msmhost_group_set_rotated(self.h, int(subject), p))
+
+    def finish_setup(self):
+        self._ck(self._L.msmhost_group_finish_setup(self.h))
+
     def fusion(self, threads=1, tables=False):
         """Fusion::optimize (the reference's, unmodified) or, tables=True, the batched FusionTables::optimize_group — only
         in libraries built with the reference's optimisers (oracle/_ref)."""

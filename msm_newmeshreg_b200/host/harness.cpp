@@ -517,6 +517,34 @@ int msmhost_metric_resample(const double* in_xyz, int nv_in, const int* in_tris,
     });
 }
 #endif
+#ifndef WITH_REF_COST
+// the 4 fusion-move costs of every inter-subject pair for proposal label alpha (include/Fusion/Fusion.h:169-172): out[P][4]
+int msmhost_group_pair_moves(void* h, const int* labeling, int alpha, double* out) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] { b->model->getGroupCostFunction()->computePairwiseMoves(labeling, alpha, out); });
+}
+// multi-GPU: this rank produces the rotated / resampled data of subjects [s0, s1) only (the S L resamplings are the expensive
+// part of setupCostFunction); the caller exchanges them (set / get below) before the patch maps are assembled
+int msmhost_group_set_subject_shard(void* h, int s0, int s1) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] { b->model->set_subject_shard(s0, s1); });
+}
+int msmhost_group_rotated_all(void* h, int subject, double* out /*[L][Vt]*/) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] {
+        const int L = b->model->getNumLabels();
+        for (int l = 0; l < L; l++) { const auto& v = b->model->rotated_mesh_values(subject, l); std::memcpy(out + (size_t)l * v.size(), v.data(), v.size() * sizeof(double)); }
+    });
+}
+int msmhost_group_set_rotated(void* h, int subject, const double* in /*[L][Vt]*/) {
+    auto* b = (GroupModelBox*)h;
+    return guard([&] { b->model->set_rotated_values(subject, in); });
+}
+int msmhost_group_finish_setup(void* h) {   // get_patch_data + set_patch_data once every subject's rotated data is in place
+    auto* b = (GroupModelBox*)h;
+    return guard([&] { b->model->finish_setup(); });
+}
+#endif
 #ifdef WITH_REF_OPTIM
 int ref_fusion_group(void* h, int threads, double* energy) {   // src/group_mesh_registration.cpp:74
     auto* b = (GroupModelBox*)h;

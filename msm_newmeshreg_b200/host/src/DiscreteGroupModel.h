@@ -78,7 +78,7 @@ public:
         estimate_pairs();
         if (FEAT && FEAT->subjects() == m_num_subjects) {   // data term (a model driven without features keeps the regulariser only)
             get_rotated_meshes();
-            get_patch_data();
+            if (shard_s0 == 0 && shard_s1 >= m_num_subjects) get_patch_data();   // sharded: after the exchange (finish_setup)
         }
         costfct->setPairs(pairs);
         costfct->setTriplets(triplets);
@@ -88,10 +88,18 @@ public:
     // index) whose range it is in — what the reference's nested loops leave behind (`rotated_mesh` is declared outside the
     // label loop, so a vertex in no range keeps its position from the previous label); `SP * R` is row vector times matrix.
     // Then metric_resample onto the template.  Only the first data row is kept: get_patch_data reads row 1 (:109).
+    // Multi-GPU (SURVEY.md §8e groupwise row): one process per GPU, subjects [s0, s1) produced here, the S L V_t resampled
+    // values exchanged by the caller (one all-gather per outer iteration), then finish_setup() on every rank.
+    void set_subject_shard(int s0, int s1) { shard_s0 = std::max(0, s0); shard_s1 = s1; }
+    void set_rotated_values(int subject, const double* in) {
+        const int Vt = m_template.nvertices();
+        for (int l = 0; l < m_num_labels; l++) rotated_values[(size_t)subject * m_num_labels + l].assign(in + (size_t)l * Vt, in + (size_t)(l + 1) * Vt);
+    }
+    void finish_setup() { get_patch_data(); }
     void get_rotated_meshes() {
         const int L = m_num_labels, N = control_grid_size;
         rotated_values.assign((size_t)m_num_subjects * L, std::vector<double>());
-        for (int s = 0; s < m_num_subjects; s++) {
+        for (int s = std::max(0, shard_s0); s < std::min(m_num_subjects, shard_s1); s++) {
             const newresampler::Mesh& data = m_datameshes[s];
             const int V = data.nvertices();
             std::vector<double> sp(N);
@@ -227,6 +235,7 @@ protected:
     std::shared_ptr<DiscreteGroupCostFunction> groupcf;
     std::vector<std::vector<double>> rotated_values;   // [subject * L + label][template vertex]: rotated_meshes, first data row
     int m_num_subjects = 0, control_grid_size = 0;
+    int shard_s0 = 0, shard_s1 = 1 << 30;
 };
 
 }  // namespace newmeshreg
