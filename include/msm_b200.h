@@ -99,6 +99,16 @@ int msm_set_group(msm_ctx* ctx, int S, int N_subj, int T_subj);
 /* get_source_data (src/DiscreteCostFunction.cpp:394-410 / :458-481): builds the per-CP patch lists for the
  * current source and CP coordinates.  Exact-tie pairs are resolved with the reference's own fp64 formula. */
 int msm_build_patches(msm_ctx* ctx);
+/* The same build without a host wait, for callers that keep the device busy (get_source_data followed by
+ * computeUnaryCosts in one outer iteration, src/mesh_registration.cpp:344-351): the kernels are enqueued and the build's
+ * one status word (boundary ties seen / a row outgrew its capacity) follows them to the host.  It is read
+ *   - by msm_unary_table / msm_get_patches / msm_patch_count on their own (they wait for the device anyway; a flagged
+ *     build is repeated through the exact path and the table recomputed before they return), or
+ *   - by msm_patches_resolve, which callers of the device-resident entry points (msm_unary_table_dev / _peers) must call
+ *     before trusting what they launched: *redone = 1 means the patches were rebuilt and those launches must be repeated.
+ * msm_build_patches == msm_build_patches_async + msm_patches_resolve. */
+int msm_build_patches_async(msm_ctx* ctx);
+int msm_patches_resolve(msm_ctx* ctx, int* redone);
 /* _sourceinrange as CSR: offsets int[N+1] (only this shard's rows are non-empty), idx int[total]. */
 int msm_patch_count(msm_ctx* ctx, long long* total);
 /* Introspection for tests/bench: how many builds of this context took the one-pass path (second and later builds of a level,

@@ -25,7 +25,7 @@ class MsmParams(C.Structure):
 EXPORTS = [
     "msm_default_params", "msm_create", "msm_destroy", "msm_last_error", "msm_set_stream", "msm_synchronize", "msm_set_params",
     "msm_set_target", "msm_set_source", "msm_reset_source", "msm_set_cpgrid", "msm_set_abs_weights", "msm_reset_cpgrid", "msm_set_shard", "msm_set_labels",
-    "msm_set_pairs", "msm_set_triplets", "msm_set_group", "msm_build_patches", "msm_patch_count", "msm_get_patches",
+    "msm_set_pairs", "msm_set_triplets", "msm_set_group", "msm_build_patches", "msm_build_patches_async", "msm_patches_resolve", "msm_patch_count", "msm_get_patches",
     "msm_unary_table", "msm_unary_table_dev", "msm_triplet_costs", "msm_triplet_table", "msm_triplet_table_dev", "msm_triplet_moves",
     "msm_triplet_moves_f32", "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count", "msm_patch_build_stats",
     "msm_set_timing", "msm_last_kernel_ms", "msm_timing_collect", "msm_set_group_patches", "msm_group_pair_costs",
@@ -187,6 +187,16 @@ class Context:
     # ---- hot path ------------------------------------------------------------------------------------------
     def build_patches(self):
         self._ck(lib().msm_build_patches(self._h))
+
+    def build_patches_async(self):
+        """get_source_data without a host wait; follow device-resident launches with patches_resolve()."""
+        self._ck(lib().msm_build_patches_async(self._h))
+
+    def patches_resolve(self):
+        """Reads the status of a deferred build; True = the patches were rebuilt (exact path): repeat the device-resident launches."""
+        r = C.c_int(0)
+        self._ck(lib().msm_patches_resolve(self._h, C.byref(r)))
+        return bool(r.value)
 
     def patches(self):
         tot = C.c_longlong()

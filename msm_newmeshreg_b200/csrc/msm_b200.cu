@@ -33,6 +33,7 @@ struct BigSmemLock {
     std::unique_lock<std::mutex> lk;
     explicit BigSmemLock(size_t smem) : lk(g_big_smem_mtx, std::defer_lock) { if (smem > 48 * 1024) lk.lock(); }
 };
+constexpr int kUncCap = 1 << 20;   // boundary-tie pairs one patch build can hand to the host
 thread_local std::string g_create_error;   // per thread: contexts may be created concurrently
 
 struct DevBuf {
@@ -136,6 +137,13 @@ struct msm_ctx {
     int pad_cap = 0;
     DevBuf d_pflags, d_end;
     long long fast_builds = 0, exact_builds = 0;
+    // deferred check of the one-pass build (msm_build_patches_async): the flag word travels to `h_pflags` behind the
+    // kernel, `ev_patch` marks its arrival; until msm_patches_resolve has read it, maxP / total are the row capacity's bounds
+    bool patch_pending = false;
+    cudaEvent_t ev_patch = nullptr;
+    PinBuf h_pflags;
+    BinGrid pend_bg{};
+    bool pend_binned = false;
 
     DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
 
@@ -359,6 +367,8 @@ PairArgs pair_args(msm_ctx* ctx) {
 
 extern "C" {
 
+static int patch_settle(msm_ctx* ctx, bool redo, int* redone);
+
 void msm_default_params(msm_params* p) {
     p->lambda = 1.0; p->rexp = 2.0; p->mu = 0.4f; p->kappa = 1.6f; p->k_exp = 2.0; p->range = 1.0;
     p->simmeasure = 2; p->rmode = 1; p->dweight = 0; p->anorm = 0; p->meanangle = 0.0; p->mvdmax = 0.0; p->group = 0;
@@ -395,6 +405,7 @@ void msm_destroy(msm_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_patch) cudaEventDestroy(ctx->ev_patch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -411,7 +422,10 @@ int msm_synchronize(msm_ctx* ctx) { CK(cudaSetDevice(ctx->device)); CK(cudaStrea
 
 int msm_set_params(msm_ctx* ctx, const msm_params* p) {
     if (p->bary_orthogonal) FAIL("bary_orthogonal: only the radial projection (A4 default) is implemented on the device");
-    if (p->range != ctx->par.range) { ctx->have_patches = false; ctx->have_unary = false; }   // patches were built for the old range
+    if (p->range != ctx->par.range) {   // patches were built for the old range
+        if (patch_settle(ctx, false, nullptr)) return 1;
+        ctx->have_patches = false; ctx->have_unary = false;
+    }
     if (p->simmeasure != ctx->par.simmeasure) ctx->have_unary = false;                        // sign of the cached table
     ctx->par = *p;
     return 0;
@@ -493,6 +507,7 @@ int msm_set_source(msm_ctx* ctx, const double* xyz, int V, const double* feat, i
     if (upload(ctx, ctx->d_sfeat, feat, (size_t)C * V)) return 1;
     CK(cudaStreamSynchronize(ctx->stream));
     if (wrows > 0 && upload_as_float(ctx, ctx->d_swgt, cfweight, (size_t)wrows * V)) return 1;
+    if (patch_settle(ctx, false, nullptr)) return 1;
     ctx->have_patches = false;
     return msm_reset_source(ctx, xyz);
 }
@@ -505,6 +520,7 @@ int msm_reset_source(msm_ctx* ctx, const double* xyz) {
     // the fp32 SoA copy used by the patch pre-filter is derived on the device
     const size_t n3 = (size_t)ctx->Vs * 3;
     CK(cudaStreamSynchronize(ctx->stream));   // a previous upload may still be reading the staging buffer
+    if (patch_settle(ctx, false, nullptr)) return 1;   // a deferred patch build of the old coordinates is retired, not repeated
     CK(ctx->h_src.ensure(n3 * sizeof(double)));
     double* hs = ctx->h_src.as<double>();
     double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
@@ -530,6 +546,7 @@ int msm_set_cpgrid(msm_ctx* ctx, const double* xyz, int N, const int* tris, int 
                    const double* abs_weights) {
     CK(cudaSetDevice(ctx->device));
     if (N <= 0) FAIL("msm_set_cpgrid: empty control grid");
+    if (patch_settle(ctx, false, nullptr)) return 1;
     ctx->N = N; ctx->Tcp = T;
     ctx->k_begin = 0; ctx->k_end = N;
     ctx->h_cp.assign(xyz, xyz + (size_t)N * 3);
@@ -576,6 +593,7 @@ int msm_set_abs_weights(msm_ctx* ctx, const double* abs_weights) {
 int msm_reset_cpgrid(msm_ctx* ctx, const double* xyz) {
     CK(cudaSetDevice(ctx->device));
     if (ctx->N <= 0) FAIL("msm_set_cpgrid must be called first");
+    if (patch_settle(ctx, false, nullptr)) return 1;   // (the exact redo of a deferred build reads h_cp)
     ctx->h_cp.assign(xyz, xyz + (size_t)ctx->N * 3);
     if (upload(ctx, ctx->d_cp, xyz, (size_t)ctx->N * 3)) return 1;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -587,6 +605,7 @@ int msm_reset_cpgrid(msm_ctx* ctx, const double* xyz) {
 
 int msm_set_shard(msm_ctx* ctx, int k_begin, int k_end) {
     if (k_begin < 0 || k_end > ctx->N || k_begin > k_end) FAIL("msm_set_shard: bad range");
+    if (patch_settle(ctx, false, nullptr)) return 1;
     ctx->k_begin = k_begin; ctx->k_end = k_end;
     ctx->have_patches = false;
     ctx->have_unary = false;
@@ -637,30 +656,62 @@ int msm_set_group(msm_ctx* ctx, int S, int N_subj, int T_subj) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-int msm_build_patches(msm_ctx* ctx) {
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->Vs <= 0 || ctx->N <= 0) FAIL("CostFunction::You must supply source and target meshes.");
-    if (ctx->h_maxsep.empty()) FAIL("msm_build_patches: set_spacings (maxsep) missing");
-    const int Ns = ctx->k_end - ctx->k_begin;
-    ctx->have_patches = false;
-    ctx->total = 0; ctx->maxP = 0;
-    if (Ns == 0) { ctx->have_patches = true; return 0; }
-    const int unc_cap = 1 << 20;
-    CK(ctx->d_counts.ensure((size_t)Ns * 4));
-    CK(ctx->d_off.ensure((size_t)(Ns + 1) * 4));
-    CK(ctx->d_unc.ensure((size_t)unc_cap * sizeof(int2)));
-    CK(ctx->d_unc_count.ensure(4));
-    CK(ctx->d_totmax.ensure(8));
-    CK(cudaMemsetAsync(ctx->d_unc_count.p, 0, 4, ctx->stream));
+static PatchArgs patch_args(msm_ctx* ctx) {
     PatchArgs a;
     a.k_begin = ctx->k_begin; a.k_end = ctx->k_end; a.V = ctx->Vs;
     a.sxf = ctx->d_sxf.as<float>(); a.syf = ctx->d_syf.as<float>(); a.szf = ctx->d_szf.as<float>();
     a.src = ctx->d_src.as<double>(); a.cp = ctx->d_cp.as<double>(); a.maxsep = ctx->d_maxsep.as<double>();
     a.range = ctx->par.range;
     a.counts = ctx->d_counts.as<int>();
-    a.unc = ctx->d_unc.as<int2>(); a.unc_cap = unc_cap; a.unc_count = ctx->d_unc_count.as<int>();
+    a.unc = ctx->d_unc.as<int2>(); a.unc_cap = kUncCap; a.unc_count = ctx->d_unc_count.as<int>();
     a.acc_off = nullptr; a.acc_idx = nullptr; a.off = nullptr; a.idx = nullptr;
     a.slab = nullptr; a.slab_cap = 0;
+    return a;
+}
+
+static int patches_exact(msm_ctx* ctx, const BinGrid& bg, bool binned);
+
+// Reads the flag word of a deferred one-pass build.  redo = true: a build that saw boundary ties or an overflowing row is
+// repeated through the exact path (the voxel grid of that build is still in place); redo = false: the inputs are about
+// to change, the build is only retired.
+static int patch_settle(msm_ctx* ctx, bool redo, int* redone) {
+    if (redone) *redone = 0;
+    if (!ctx->patch_pending) return 0;
+    CK(cudaEventSynchronize(ctx->ev_patch));
+    ctx->patch_pending = false;
+    const int* hf = ctx->h_pflags.as<int>();
+    if (hf[0] == 0 && hf[1] == 0) {
+        ctx->total = hf[3]; ctx->maxP = hf[2];
+        const long long want = (long long)ctx->maxP + ctx->maxP / 4 + 16;
+        ctx->slab_cap = (int)std::max<long long>(want, 32);
+        ctx->fast_builds++;
+        return 0;
+    }
+    ctx->have_patches = false;
+    ctx->have_unary = false;
+    if (!redo) return 0;
+    if (redone) *redone = 1;
+    Timer tm(ctx, "patches");
+    CK(cudaMemsetAsync(ctx->d_unc_count.p, 0, 4, ctx->stream));
+    return patches_exact(ctx, ctx->pend_bg, ctx->pend_binned);
+}
+
+int msm_build_patches_async(msm_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->Vs <= 0 || ctx->N <= 0) FAIL("CostFunction::You must supply source and target meshes.");
+    if (ctx->h_maxsep.empty()) FAIL("msm_build_patches: set_spacings (maxsep) missing");
+    if (patch_settle(ctx, false, nullptr)) return 1;   // retire the previous build (its largest patch sizes this one's rows)
+    const int Ns = ctx->k_end - ctx->k_begin;
+    ctx->have_patches = false;
+    ctx->total = 0; ctx->maxP = 0;
+    if (Ns == 0) { ctx->have_patches = true; return 0; }
+    CK(ctx->d_counts.ensure((size_t)Ns * 4));
+    CK(ctx->d_off.ensure((size_t)(Ns + 1) * 4));
+    CK(ctx->d_unc.ensure((size_t)kUncCap * sizeof(int2)));
+    CK(ctx->d_unc_count.ensure(4));
+    CK(ctx->d_totmax.ensure(8));
+    CK(cudaMemsetAsync(ctx->d_unc_count.p, 0, 4, ctx->stream));
+    const PatchArgs a = patch_args(ctx);
     Timer tm(ctx, "patches");
     // voxel grid over the source vertices (cell >= largest patch chord); brute force only for degenerate sizes
     BinGrid bg{};
@@ -748,23 +799,40 @@ int msm_build_patches(msm_ctx* ctx) {
 #undef PATCH_FUSED
             }
             KLAUNCH_CHECK();
-            CK(ctx->h_pin.ensure(16));
-            int* hf = ctx->h_pin.as<int>();
-            CK(cudaMemcpyAsync(hf, ctx->d_pflags.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            if (hf[0] == 0 && hf[1] == 0) {
-                ctx->total = hf[3]; ctx->maxP = hf[2];
-                ctx->pack_cp = Cp;
-                ctx->patches_padded = true; ctx->pad_cap = cap;
-                const long long want = (long long)ctx->maxP + ctx->maxP / 4 + 16;
-                ctx->slab_cap = (int)std::max<long long>(want, 32);
-                ctx->have_patches = true;
-                ctx->have_unary = false;
-                ctx->fast_builds++;
-                return 0;
-            }
+            // the flag word follows the kernel to the host; nobody waits for it here (msm_patches_resolve / the host-output
+            // entry points do).  Until then the row capacity bounds the sizes the launches below need.
+            CK(ctx->h_pflags.ensure(16));
+            if (!ctx->ev_patch) CK(cudaEventCreateWithFlags(&ctx->ev_patch, cudaEventDisableTiming));
+            CK(cudaMemcpyAsync(ctx->h_pflags.p, ctx->d_pflags.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaEventRecord(ctx->ev_patch, ctx->stream));
+            ctx->patch_pending = true;
+            ctx->pend_bg = bg; ctx->pend_binned = binned;
+            ctx->total = (long long)Ns * cap; ctx->maxP = cap;
+            ctx->pack_cp = Cp;
+            ctx->patches_padded = true; ctx->pad_cap = cap;
+            ctx->have_patches = true;
+            ctx->have_unary = false;
+            return 0;
         }
     }
+    return patches_exact(ctx, bg, binned);
+}
+
+int msm_patches_resolve(msm_ctx* ctx, int* redone) {
+    CK(cudaSetDevice(ctx->device));
+    return patch_settle(ctx, true, redone);
+}
+
+int msm_build_patches(msm_ctx* ctx) {
+    if (msm_build_patches_async(ctx)) return 1;
+    return patch_settle(ctx, true, nullptr);
+}
+
+// The exact two-pass path: first build of a level, boundary ties, rows that outgrew their capacity.
+static int patches_exact(msm_ctx* ctx, const BinGrid& bg, bool binned) {
+    const int Ns = ctx->k_end - ctx->k_begin;
+    const int unc_cap = kUncCap;
+    PatchArgs a = patch_args(ctx);
     ctx->patches_padded = false;
     ctx->exact_builds++;
     // Patches change little between outer iterations: from the second build on, the count pass stashes the members it finds
@@ -876,6 +944,7 @@ int msm_build_patches(msm_ctx* ctx) {
 }
 
 int msm_patch_count(msm_ctx* ctx, long long* total) {
+    if (patch_settle(ctx, true, nullptr)) return 1;
     if (!ctx->have_patches) FAIL("msm_build_patches must be called first");
     *total = ctx->total;
     return 0;
@@ -888,6 +957,7 @@ int msm_patch_build_stats(const msm_ctx* ctx, long long* one_pass, long long* tw
 
 int msm_get_patches(msm_ctx* ctx, int* offsets, int* idx) {
     CK(cudaSetDevice(ctx->device));
+    if (patch_settle(ctx, true, nullptr)) return 1;
     if (!ctx->have_patches) FAIL("msm_build_patches must be called first");
     const int Ns = ctx->k_end - ctx->k_begin;
     std::vector<int> off(Ns + 1, 0);
@@ -1040,6 +1110,15 @@ int msm_unary_table(msm_ctx* ctx, double* out) {
     CK(ctx->h_pin.ensure((size_t)L * Ns * 4));
     CK(cudaMemcpyAsync(ctx->h_pin.p, ctx->d_unary.p, (size_t)L * Ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    {   // a deferred patch build is checked here, where the host waits anyway; the rare repeat recomputes the table
+        int redone = 0;
+        if (patch_settle(ctx, true, &redone)) return 1;
+        if (redone) {
+            if (msm_unary_table_dev(ctx, ctx->d_unary.as<float>())) return 1;
+            CK(cudaMemcpyAsync(ctx->h_pin.p, ctx->d_unary.p, (size_t)L * Ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     const float* h = ctx->h_pin.as<float>();
     for (int l = 0; l < L; l++) {
         double* o = out + (size_t)l * N + ctx->k_begin;

@@ -207,7 +207,7 @@ public:
     virtual void get_source_data() {  // :394-410 / :458-481 : patches, then the whole unary table in one launch
         { HostTimer t("    sync_device_state"); sync_device_state(); }
         { HostTimer t("    resample_weights"); resample_weights(); }
-        { HostTimer t("    msm_build_patches"); check(msm_build_patches(ctx)); }
+        { HostTimer t("    msm_build_patches"); check(msm_build_patches_async(ctx)); }   // status read by msm_unary_table below
         unary_pristine.resize((size_t)m_num_labels * m_num_nodes);   // every entry is written by msm_unary_table
         { HostTimer t("    msm_unary_table"); check(msm_unary_table(ctx, unary_pristine.data())); }
         unary_epoch = tables_epoch.load();

@@ -115,6 +115,68 @@ def test_patch_rebuild_paths_give_identical_lists(built, warp):
         c1.close()
 
 
+def test_deferred_patch_build_matches_synchronous_build(built):
+    """msm_build_patches_async + device-resident table + msm_patches_resolve: same table bits as the synchronous build, and a
+    flagged build (boundary ties of the undeformed icosphere, a row that outgrew its capacity) reports `redone`, after which the
+    repeated launch gives the exact path's table.  Host-output entry points resolve on their own."""
+    import torch
+    P = pb.make_problem(5, 3, 1, seed=9, warp=0.3, deform_cp=0.1)
+    Q = pb.make_problem(5, 3, 1, seed=9, warp=0.0, deform_cp=0.0)     # undeformed: exact ties at range 1
+
+    def fresh(sxyz, cxyz, r):
+        c = pb.gpu_context(P, params=dict(rng=pb.f32(r)))
+        c.reset_source(sxyz); c.reset_cpgrid(cxyz); c.build_patches()
+        out = c.patches() + (c.unary_table(),)
+        c.close()
+        return out
+
+    ctx = pb.gpu_context(P)
+    d_out = torch.empty((ctx.L, ctx.N), dtype=torch.float32, device="cuda")
+
+    def dev_table():
+        ctx.unary_table_dev(d_out.data_ptr()); ctx.synchronize()
+        return d_out.cpu().numpy().astype(np.float64)
+
+    ref = fresh(P.sxyz, P.cxyz, 1.0)
+    ctx.build_patches_async()                                    # first build of the context: exact path, nothing deferred
+    assert not ctx.patches_resolve()
+    assert np.array_equal(dev_table(), ref[2])
+    ctx.build_patches_async()                                    # one-pass build, status word still in flight
+    t = dev_table()
+    assert not ctx.patches_resolve()
+    assert np.array_equal(t, ref[2]) and ctx.patch_build_stats() == (1, 1)
+    off, idx = ctx.patches()
+    assert np.array_equal(off, ref[0]) and np.array_equal(idx, ref[1])
+    # ties: the one-pass build is flagged, resolve repeats it through the exact path and says so
+    ctx.reset_source(Q.sxyz); ctx.reset_cpgrid(Q.cxyz)
+    refq = fresh(Q.sxyz, Q.cxyz, 1.0)
+    ctx.build_patches_async()
+    dev_table()                                                  # computed from a flagged build: not to be trusted
+    assert ctx.patches_resolve()
+    assert np.array_equal(dev_table(), refq[2])
+    off, idx = ctx.patches()
+    assert np.array_equal(off, refq[0]) and np.array_equal(idx, refq[1])
+    # the host-output table resolves on its own (and recomputes)
+    ctx.build_patches_async()
+    assert np.array_equal(ctx.unary_table(), refq[2])
+    assert not ctx.patches_resolve()
+    # a deferred build whose inputs change before anybody looked is simply retired
+    ctx.reset_source(P.sxyz); ctx.reset_cpgrid(P.cxyz)
+    ctx.build_patches_async()
+    ctx.reset_source(Q.sxyz); ctx.reset_cpgrid(Q.cxyz)
+    ctx.build_patches_async()
+    assert np.array_equal(ctx.unary_table(), refq[2])
+    # row overflow: patches 4-5x larger than the rows sized by the previous build
+    ctx.reset_source(P.sxyz); ctx.reset_cpgrid(P.cxyz)
+    ctx.build_patches()
+    _set_range(ctx, P, 1.5)
+    ctx.build_patches_async()
+    dev_table()
+    assert ctx.patches_resolve()
+    assert np.array_equal(dev_table(), fresh(P.sxyz, P.cxyz, 1.5)[2])
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ unary
 @pytest.mark.parametrize("kw", [
     dict(data_level=4, cp_level=2, C=1, warp=0.3),
