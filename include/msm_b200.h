@@ -179,6 +179,25 @@ int msm_locate(msm_ctx* ctx, const double* pts, int M, int* tri, double* w);
 int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* from_xyz, int V, const int* tris, int F,
                          const double* to_xyz, double radius, double* out, int* tri_out, double* w_out);
 
+/* ---- Feature pre-processing per resolution level (featurespace::initialize, src/featurespace.cc:18-65).  All arrays are
+ * caller-owned host doubles, data as [D][V] (dimension-major, the transpose-free layout of BFMatrix rows); masks hold > 0 for
+ * "use", <= 0 for "excluded".  The context only supplies the device, the stream and the error string.
+ *
+ * msm_smooth_data      : newresampler::smooth_data(in, ref, sigma, threads, EXCL) ([EXT] A9, call site src/featurespace.cc:49):
+ *                        out[d][k] = sum_j w_kj values[d][j] / sum_j w_kj over the `in` vertices j within 2 asin(sigma / RAD) of ref
+ *                        vertex k, w = exp(-geodesic^2 / 2 sigma^2); mask [Vin] or NULL; 0 where nothing is in range.
+ * msm_histogram_match  : multivariate_histogram_normalization (src/reg_tools.cpp:750-810) over MISCMATHS::Histogram ([EXT] A10):
+ *                        every dimension of `data` [D][V] is matched IN PLACE to the same dimension of data_ref [D][Vref];
+ *                        excl / excl_ref: NULL or [rows][V] — row d when rows > d, else row 0 (:771-776); bins = 256 in the reference.
+ * msm_variance_normalise: featurespace::variance_normalise (src/featurespace.cc:67-108), in place, mask [V] or NULL.
+ * msm_create_exclusion : newresampler::create_exclusion ([EXT] A11, call site src/featurespace.cc:42): mask_out[V]. */
+int msm_smooth_data(msm_ctx* ctx, const double* in_xyz, int Vin, const double* values, int D, const double* mask, const double* ref_xyz, int Vref,
+                    double sigma, double* out);
+int msm_histogram_match(msm_ctx* ctx, double* data, int V, const double* data_ref, int Vref, int D, const double* excl, int excl_rows,
+                        const double* excl_ref, int excl_ref_rows, int bins);
+int msm_variance_normalise(msm_ctx* ctx, double* data, int D, int V, const double* mask);
+int msm_create_exclusion(msm_ctx* ctx, const double* data, int D, int V, float lower, float upper, double* mask_out);
+
 /* evaluateTotalCostSum (src/DiscreteCostFunction.cpp:41-70) from the device tables of the last *_table calls:
  * sums[0..2] = unary, pairwise, triplet; requires msm_unary_table(_dev) to have run. */
 int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]);

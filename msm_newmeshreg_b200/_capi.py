@@ -30,6 +30,7 @@ EXPORTS = [
     "msm_triplet_moves_f32", "msm_triplet_moves_dev", "msm_triplet_moves_range_dev", "msm_unary_table_peers", "msm_triplet_moves_range_peers", "msm_pair_table", "msm_pair_table_dev", "msm_locate", "msm_total_cost", "msm_launch_count", "msm_patch_build_stats",
     "msm_set_timing", "msm_last_kernel_ms", "msm_timing_collect", "msm_set_group_patches", "msm_group_pair_costs",
     "msm_group_pair_moves", "msm_group_pair_table", "msm_mesh_interpolate",
+    "msm_smooth_data", "msm_histogram_match", "msm_variance_normalise", "msm_create_exclusion",
 ]
 
 _lib = None
@@ -287,6 +288,44 @@ class Context:
             return out, tri, w
         self._ck(lib().msm_mesh_interpolate(self._h, pp, len(pts), pf, len(from_xyz), pt, len(tris), po, C.c_double(radius),
                                             out.ctypes.data_as(c_dp), None, None))
+        return out
+
+    # ---- feature pre-processing (src/featurespace.cc:18-108) ------------------------------------------------
+    @staticmethod
+    def _mask(m, n):
+        if m is None:
+            return None, None, 0
+        m = np.ascontiguousarray(np.atleast_2d(m), dtype=np.float64)
+        assert m.shape[1] == n
+        return m, m.ctypes.data_as(c_dp), m.shape[0]
+
+    def smooth_data(self, in_xyz, values, ref_xyz, sigma, mask=None):
+        in_xyz, p1 = _d(in_xyz); values = np.atleast_2d(values); values, p2 = _d(values); ref_xyz, p3 = _d(ref_xyz)
+        assert values.shape[1] == len(in_xyz)
+        m, pm, _ = self._mask(mask, len(in_xyz))
+        out = np.empty((values.shape[0], len(ref_xyz)))
+        self._ck(lib().msm_smooth_data(self._h, p1, len(in_xyz), p2, values.shape[0], pm, p3, len(ref_xyz), C.c_double(sigma),
+                                       out.ctypes.data_as(c_dp)))
+        return out
+
+    def histogram_match(self, data, data_ref, excl=None, excl_ref=None, bins=256):
+        a = np.array(np.atleast_2d(data), dtype=np.float64, order="C", copy=True)
+        b, pb_ = _d(np.atleast_2d(data_ref))
+        assert a.shape[0] == b.shape[0]
+        ea, pea, ra = self._mask(excl, a.shape[1]); eb, peb, rb = self._mask(excl_ref, b.shape[1])
+        self._ck(lib().msm_histogram_match(self._h, a.ctypes.data_as(c_dp), a.shape[1], pb_, b.shape[1], a.shape[0], pea, ra, peb, rb, int(bins)))
+        return a
+
+    def variance_normalise(self, data, mask=None):
+        a = np.array(np.atleast_2d(data), dtype=np.float64, order="C", copy=True)
+        m, pm, _ = self._mask(mask, a.shape[1])
+        self._ck(lib().msm_variance_normalise(self._h, a.ctypes.data_as(c_dp), a.shape[0], a.shape[1], pm))
+        return a
+
+    def create_exclusion(self, data, lower, upper):
+        a, pa = _d(np.atleast_2d(data))
+        out = np.empty(a.shape[1])
+        self._ck(lib().msm_create_exclusion(self._h, pa, a.shape[0], a.shape[1], C.c_float(lower), C.c_float(upper), out.ctypes.data_as(c_dp)))
         return out
 
     def total_cost(self, labeling):

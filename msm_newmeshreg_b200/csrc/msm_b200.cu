@@ -20,6 +20,7 @@
 #include "meshwarp.cuh"
 #include "triplet.cuh"
 #include "patchfast.cuh"
+#include "features.cuh"
 
 using namespace msm;
 
@@ -146,6 +147,9 @@ struct msm_ctx {
     bool pend_binned = false;
 
     DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
+    // feature pre-processing (features.cuh): scratch of its own, so that a deferred patch build's voxel grid stays intact
+    DevBuf d_f_in, d_f_ref, d_f_vals, d_f_mask, d_f_mask2, d_f_out, d_f_stats, d_f_cdf;
+    DevBuf d_f_cell_counts, d_f_cell_start, d_f_cell_fill, d_f_cell_of, d_f_sorted, d_f_sorted2, d_f_scan;
 
     // outputs / scratch
     DevBuf d_unary, d_scratch, d_scratch2, d_tprep;
@@ -1506,6 +1510,123 @@ int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* f
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------
+// Feature pre-processing (src/featurespace.cc:18-108, src/reg_tools.cpp:750-810) — features.cuh
+int msm_smooth_data(msm_ctx* ctx, const double* in_xyz, int Vin, const double* values, int D, const double* mask, const double* ref_xyz, int Vref,
+                    double sigma, double* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (Vin <= 0 || Vref <= 0 || D <= 0) FAIL("msm_smooth_data: empty input");
+    if (!(sigma > 0.0)) FAIL("msm_smooth_data: sigma must be positive (the caller skips the smoothing otherwise, src/featurespace.cc:48)");
+    const double RAD = 100.0;
+    const double chord_max = 2.0 * RAD * std::sin(std::asin(std::min(1.0, sigma / RAD)));   // angular support 2 asin(sigma / RAD)
+    double bound = 0.0;
+    for (size_t i = 0; i < (size_t)Vin * 3; i++) bound = std::max(bound, std::fabs(in_xyz[i]));
+    bound = bound * (1.0 + 1e-9) + 1e-6;
+    const int G = std::max(1, std::min(64, (int)std::floor(2.0 * bound / std::max(chord_max, 1e-9))));
+    const size_t nc = (size_t)G * G * G;
+    if (upload(ctx, ctx->d_f_in, in_xyz, (size_t)Vin * 3)) return 1;
+    if (upload(ctx, ctx->d_f_ref, ref_xyz, (size_t)Vref * 3)) return 1;
+    if (upload(ctx, ctx->d_f_vals, values, (size_t)D * Vin)) return 1;
+    if (mask && upload(ctx, ctx->d_f_mask, mask, (size_t)Vin)) return 1;
+    CK(ctx->d_f_out.ensure((size_t)D * Vref * 8));
+    CK(ctx->d_f_cell_counts.ensure(nc * 4)); CK(ctx->d_f_cell_start.ensure((nc + 1) * 4)); CK(ctx->d_f_cell_fill.ensure(nc * 4));
+    CK(ctx->d_f_cell_of.ensure((size_t)Vin * 4)); CK(ctx->d_f_sorted.ensure((size_t)Vin * 4)); CK(ctx->d_f_sorted2.ensure((size_t)Vin * 4));
+    CK(cudaMemsetAsync(ctx->d_f_cell_counts.p, 0, nc * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_f_cell_fill.p, 0, nc * 4, ctx->stream));
+    {
+    Timer tm(ctx, "smooth");
+    BinGrid bg{};
+    bg.G = G; bg.lo = -bound; bg.inv_h = G / (2.0 * bound);
+    bg.cell_start = ctx->d_f_cell_start.as<int>(); bg.cell_fill = ctx->d_f_cell_fill.as<int>(); bg.sorted = ctx->d_f_sorted.as<int>();
+    k_bin_count<<<(Vin + 255) / 256, 256, 0, ctx->stream>>>(bg, Vin, ctx->d_f_in.as<double>(), ctx->d_f_cell_of.as<int>(), ctx->d_f_cell_counts.as<int>());
+    KLAUNCH_CHECK();
+    {
+        const int nchunks = 148, chunk = ((int)nc + nchunks - 1) / nchunks;
+        CK(ctx->d_f_scan.ensure((size_t)nchunks * 4));
+        k_scan_chunk_sums<<<nchunks, 256, 0, ctx->stream>>>((int)nc, chunk, ctx->d_f_cell_counts.as<int>(), ctx->d_f_scan.as<int>());
+        KLAUNCH_CHECK();
+        k_scan_chunk_apply<<<nchunks, 256, 0, ctx->stream>>>((int)nc, chunk, ctx->d_f_cell_counts.as<int>(), ctx->d_f_scan.as<int>(),
+                                                            ctx->d_f_cell_start.as<int>());
+        KLAUNCH_CHECK();
+    }
+    k_bin_fill<<<(Vin + 255) / 256, 256, 0, ctx->stream>>>(bg, Vin, ctx->d_f_cell_of.as<int>());
+    KLAUNCH_CHECK();
+    k_cell_rank_sort<<<(unsigned)((nc + 3) / 4), 128, 0, ctx->stream>>>((int)nc, bg.cell_start, ctx->d_f_sorted.as<int>(), ctx->d_f_sorted2.as<int>());
+    KLAUNCH_CHECK();
+    bg.sorted = ctx->d_f_sorted2.as<int>();
+    SmoothArgs a;
+    a.g = bg; a.Vin = Vin; a.Vref = Vref; a.D = D;
+    a.in_xyz = ctx->d_f_in.as<double>(); a.ref_xyz = ctx->d_f_ref.as<double>(); a.values = ctx->d_f_vals.as<double>();
+    a.mask = mask ? ctx->d_f_mask.as<double>() : nullptr;
+    a.chord_max = chord_max; a.sigma = sigma; a.out = ctx->d_f_out.as<double>();
+    const unsigned grid = (unsigned)((Vref + 3) / 4);
+    if (D == 1) k_smooth<1><<<grid, 128, 0, ctx->stream>>>(a);
+    else if (D == 2) k_smooth<2><<<grid, 128, 0, ctx->stream>>>(a);
+    else k_smooth<4><<<grid, 128, 0, ctx->stream>>>(a);
+    KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(out, ctx->d_f_out.p, (size_t)D * Vref * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_histogram_match(msm_ctx* ctx, double* data, int V, const double* data_ref, int Vref, int D, const double* excl, int excl_rows,
+                        const double* excl_ref, int excl_ref_rows, int bins) {
+    CK(cudaSetDevice(ctx->device));
+    if (V <= 0 || Vref <= 0 || D <= 0) FAIL("msm_histogram_match: empty input");
+    if (bins < 2 || bins > 4096) FAIL("msm_histogram_match: bins must be in [2, 4096]");
+    if (V >= (1 << 24) || Vref >= (1 << 24)) FAIL("msm_histogram_match: more than 2^24 values per dimension (the reference counts them in a float)");
+    if ((excl && excl_rows < 1) || (excl_ref && excl_ref_rows < 1)) FAIL("msm_histogram_match: mask rows");
+    if (upload(ctx, ctx->d_f_vals, data, (size_t)D * V)) return 1;
+    if (upload(ctx, ctx->d_f_ref, data_ref, (size_t)D * Vref)) return 1;
+    if (excl && upload(ctx, ctx->d_f_mask, excl, (size_t)excl_rows * V)) return 1;
+    if (excl_ref && upload(ctx, ctx->d_f_mask2, excl_ref, (size_t)excl_ref_rows * Vref)) return 1;
+    CK(ctx->d_f_stats.ensure((size_t)2 * D * sizeof(HistStats)));
+    CK(ctx->d_f_cdf.ensure((size_t)2 * D * bins * 8));
+    {
+    Timer tm(ctx, "histmatch");
+    k_hist_stats<<<2 * D, 1024, (size_t)bins * 4, ctx->stream>>>(D, bins, ctx->d_f_vals.as<double>(), V, excl ? ctx->d_f_mask.as<double>() : nullptr,
+                                                                excl_rows, ctx->d_f_ref.as<double>(), Vref,
+                                                                excl_ref ? ctx->d_f_mask2.as<double>() : nullptr, excl_ref_rows,
+                                                                ctx->d_f_stats.as<HistStats>(), ctx->d_f_cdf.as<double>());
+    KLAUNCH_CHECK();
+    k_hist_match<<<dim3((unsigned)((V + 255) / 256), (unsigned)D), 256, (size_t)2 * bins * 8, ctx->stream>>>(
+        D, bins, ctx->d_f_vals.as<double>(), V, excl ? ctx->d_f_mask.as<double>() : nullptr, excl_rows, ctx->d_f_stats.as<HistStats>(),
+        ctx->d_f_cdf.as<double>());
+    KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(data, ctx->d_f_vals.p, (size_t)D * V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_variance_normalise(msm_ctx* ctx, double* data, int D, int V, const double* mask) {
+    CK(cudaSetDevice(ctx->device));
+    if (V <= 0 || D <= 0) FAIL("msm_variance_normalise: empty input");
+    if (upload(ctx, ctx->d_f_vals, data, (size_t)D * V)) return 1;
+    if (mask && upload(ctx, ctx->d_f_mask, mask, (size_t)V)) return 1;
+    {
+        Timer tm(ctx, "varnorm");
+        k_varnorm<<<D, 1024, 0, ctx->stream>>>(V, ctx->d_f_vals.as<double>(), mask ? ctx->d_f_mask.as<double>() : nullptr);
+        KLAUNCH_CHECK();
+    }
+    CK(cudaMemcpyAsync(data, ctx->d_f_vals.p, (size_t)D * V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int msm_create_exclusion(msm_ctx* ctx, const double* data, int D, int V, float lower, float upper, double* mask_out) {
+    CK(cudaSetDevice(ctx->device));
+    if (V <= 0 || D <= 0) FAIL("msm_create_exclusion: empty input");
+    if (upload(ctx, ctx->d_f_vals, data, (size_t)D * V)) return 1;
+    CK(ctx->d_f_mask.ensure((size_t)V * 8));
+    k_exclusion<<<(V + 255) / 256, 256, 0, ctx->stream>>>(D, V, ctx->d_f_vals.as<double>(), (double)lower, (double)upper, ctx->d_f_mask.as<double>());
+    KLAUNCH_CHECK();
+    CK(cudaMemcpyAsync(mask_out, ctx->d_f_mask.p, (size_t)V * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int msm_total_cost(msm_ctx* ctx, const int* labeling, double sums[3]) {
     CK(cudaSetDevice(ctx->device));
     sums[0] = sums[1] = sums[2] = 0.0;

@@ -86,6 +86,29 @@ def metric_resample(in_xyz, in_tris, values, ref_xyz, ref_tris, _lib_override=No
     return out
 
 
+def featurespace_initialize(ico, mesh_in, data_in, mesh_ref, data_ref, sigma=(5.0, 5.0), thresholds=(0.0, 0.0), intensitynorm=False,
+                            varnorm=False, cut=False, exclude=False):
+    """newmeshreg::featurespace + initialize(ico, IN, exclude) (src/featurespace.cc:18-65), every step on the GPU.
+    mesh_* = (xyz, tris); data_* = [D][V].  Returns (DATA[0], DATA[1], EXCL[0] or None, EXCL[1] or None), data as [D][V_template]."""
+    L = lib()
+    x0, p0 = _d(mesh_in[0]); t0, q0 = _i(mesh_in[1]); x1, p1 = _d(mesh_ref[0]); t1, q1 = _i(mesh_ref[1])
+    d0, pd0 = _d(np.atleast_2d(data_in)); d1, pd1 = _d(np.atleast_2d(data_ref))
+    D = d0.shape[0]
+    assert d0.shape == (D, len(x0)) and d1.shape == (D, len(x1))
+    v0, v1 = (10 * 4 ** ico + 2,) * 2 if ico > 0 else (len(x0), len(x1))
+    o0, o1 = np.empty((D, v0)), np.empty((D, v1))
+    e0, e1 = np.full(len(x0), np.nan), np.full(len(x1), np.nan)
+    L.msmhost_featurespace_initialize.restype = C.c_int
+    rc = L.msmhost_featurespace_initialize(int(ico), p0, len(x0), q0, len(t0), pd0, p1, len(x1), q1, len(t1), pd1, D, C.c_double(sigma[0]),
+                                           C.c_double(sigma[1]), C.c_float(thresholds[0]), C.c_float(thresholds[1]), int(intensitynorm),
+                                           int(varnorm), int(cut), int(exclude), 1, o0.ctypes.data_as(c_dp), o1.ctypes.data_as(c_dp),
+                                           e0.ctypes.data_as(c_dp), e1.ctypes.data_as(c_dp))
+    if rc < 0:
+        raise HostError(L.msmhost_last_error().decode())
+    has = exclude or cut
+    return o0, o1, (e0 if has else None), (e1 if has else None)
+
+
 def unfold(xyz, tris, _lib_override=None):
     """newmeshreg::unfold (src/reg_tools.cpp:134-181), host side."""
     L = _lib_override or lib()

@@ -502,6 +502,32 @@ int msmhost_group_apply_labeling(void* h, double* cpgrids) {
     });
 }
 #ifndef WITH_REF_COST
+// featurespace(datain, dataref) + setters + initialize(ico, IN, exclude) (src/featurespace.cc:18-65) on raw arrays; same
+// signature as oracle/ref_feat_driver.cpp drives the reference's own class with.  Returns the template's vertex count, -1 on error.
+int msmhost_featurespace_initialize(int ico, const double* xyz0, int nv0, const int* tris0, int nf0, const double* data0, const double* xyz1, int nv1,
+                                    const int* tris1, int nf1, const double* data1, int dims, double sigma0, double sigma1, float thr_lower,
+                                    float thr_upper, int intensitynorm, int varnorm, int cut, int exclude, int threads, double* out0,
+                                    double* out1, double* excl0, double* excl1) {
+    int nv = -1;
+    const int rc = guard([&] {
+        std::vector<newresampler::Mesh> IN = {mesh_from(xyz0, nv0, tris0, nf0), mesh_from(xyz1, nv1, tris1, nf1)};
+        featurespace fs(data0, nv0, data1, nv1, dims);
+        fs.set_smoothing_parameters({sigma0, sigma1});
+        fs.set_cutthreshold({thr_lower, thr_upper});
+        fs.varnorm(varnorm != 0);
+        fs.intensitynormalize(intensitynorm != 0, cut != 0);
+        fs.set_nthreads(threads);
+        const newresampler::Mesh t = fs.initialize(ico, IN, exclude != 0);
+        std::memcpy(out0, fs.input_data(), (size_t)dims * fs.input_vertices() * sizeof(double));
+        std::memcpy(out1, fs.ref_data(), (size_t)dims * fs.ref_vertices() * sizeof(double));
+        if (excl0 && fs.get_input_excl()) std::memcpy(excl0, fs.get_input_excl()->data(), fs.get_input_excl()->size() * sizeof(double));
+        if (excl1 && fs.get_reference_excl()) std::memcpy(excl1, fs.get_reference_excl()->data(), fs.get_reference_excl()->size() * sizeof(double));
+        nv = t.nvertices();
+    });
+    return rc == 0 ? nv : -1;
+}
+#endif
+#ifndef WITH_REF_COST
 // rotated_meshes[subject * L + label] (src/DiscreteGroupModel.cpp:92), first data row, on the template's vertices
 int msmhost_group_rotated(void* h, int subject, int label, double* out) {
     auto* b = (GroupModelBox*)h;

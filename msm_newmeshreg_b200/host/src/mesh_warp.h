@@ -143,6 +143,27 @@ inline std::vector<double> metric_resample(const Mesh& in, const double* values,
     return out;
 }
 
+// metric_resample(in, ref, threads, EXCL) with an exclusion mask over the `in` vertices (src/featurespace.cc:46): excluded sources
+// (mask <= 0) drop out of every weight list, the rest is renormalised, a vertex left without sources gets 0.  mask == nullptr:
+// the plain call above.
+inline std::vector<double> metric_resample_excl(const Mesh& in, const double* values, int dims, const Mesh& ref, const double* mask) {
+    if (!mask) return metric_resample(in, values, dims, ref);
+    const ResampleWeights R = adaptive_barycentric_weights(in, ref);
+    const int Vin = in.nvertices(), Vref = ref.nvertices();
+    std::vector<double> out((size_t)dims * Vref, 0.0);
+    for (int k = 0; k < Vref; k++) {
+        double sum = 0.0;
+        for (int e = R.off[k]; e < R.off[k + 1]; e++) if (mask[R.src[e]] > 0.0) sum += R.w[e];
+        if (sum == 0.0) continue;
+        for (int d = 0; d < dims; d++) {
+            double v = 0.0;
+            for (int e = R.off[k]; e < R.off[k + 1]; e++) if (mask[R.src[e]] > 0.0) v += (R.w[e] / sum) * values[(size_t)d * Vin + R.src[e]];
+            out[(size_t)d * Vref + k] = v;
+        }
+    }
+    return out;
+}
+
 // within_controlpt_range for many centres at once (src/DiscreteCostFunction.cpp:104-109, src/DiscreteGroupModel.cpp:88,107):
 // for every centre k the points i with 2 RAD asin(|c_k - p_i| / 2 RAD) < range * spacing[k], ascending — the patch
 // construction kernels of the cost function (exact at ties), on a context of their own.  CSR: off[ncentres+1], idx.

@@ -30,7 +30,10 @@
 #include <variant>
 #include <vector>
 
+#include <functional>
+
 #include "../geom.h"
+#include "../feat.h"
 
 // ---------------------------------------------------------------------------------------------------------------
 // boost::variant / boost::get over std::variant (src/reg_tools.h:7-8,12-13)
@@ -257,18 +260,28 @@ public:
     explicit SparseBFMatrix(const SpMat<T>&) { throw std::runtime_error("fsl_ext: SparseBFMatrix is not provided"); }
 };
 
-class Histogram {  // intensity normalisation (src/reg_tools.cpp:770-810) is a pre-processing step outside the path
+// A10: MISCMATHS::Histogram as restated in oracle/feat.h (orc::Histogram) — the calls of src/reg_tools.cpp:792-806
+class Histogram {
 public:
     Histogram() = default;
-    Histogram(const NEWMAT::ColumnVector&, int) {}
-    void generate() { fail(); }
-    void generate(const NEWMAT::ColumnVector&) { fail(); }
-    void generateCDF() { fail(); }
-    void setexclusion(const NEWMAT::ColumnVector&) { fail(); }
-    void match(Histogram&) { fail(); }
-    NEWMAT::ColumnVector getsourceData() { fail(); return {}; }
+    Histogram(const NEWMAT::ColumnVector& data, int bins) : h_(std::make_shared<orc::Histogram>(vec(data), bins)) {}
+    void generate() { h_->generate(std::vector<double>(h_->source.size(), 1.0)); }
+    void generate(const NEWMAT::ColumnVector& exclude) { h_->generate(vec(exclude)); }
+    void generateCDF() { h_->generate_cdf(); }
+    void setexclusion(const NEWMAT::ColumnVector& exclude) { h_->excl = vec(exclude); }
+    void match(Histogram& target) { h_->match(*target.h_); }
+    NEWMAT::ColumnVector getsourceData() const {
+        NEWMAT::ColumnVector v((int)h_->source.size());
+        for (int i = 1; i <= v.Nrows(); i++) v(i) = h_->source[i - 1];
+        return v;
+    }
 private:
-    static void fail() { throw std::runtime_error("fsl_ext: MISCMATHS::Histogram is not provided"); }
+    static std::vector<double> vec(const NEWMAT::ColumnVector& c) {
+        std::vector<double> v(c.Nrows());
+        for (int i = 1; i <= c.Nrows(); i++) v[i - 1] = c(i);
+        return v;
+    }
+    std::shared_ptr<orc::Histogram> h_;
 };
 
 }  // namespace MISCMATHS
@@ -403,7 +416,12 @@ public:
     void set_pvalues(const NEWMAT::Matrix& M) { pv_ = M; }
     NEWMAT::Matrix get_pvalues() const { return pv_; }
     void save(const std::string&) const {}
-    void load(const std::string&, bool = true, bool = true) { throw MeshException("fsl_ext: mesh file I/O is not provided"); }
+    // no file I/O: "loading" asks the in-memory registry a test harness may have installed (oracle/ref_feat_driver.cpp)
+    static std::function<void(Mesh&, const std::string&)>& loader() { static std::function<void(Mesh&, const std::string&)> f; return f; }
+    void load(const std::string& name, bool = true, bool = true) {
+        if (!loader()) throw MeshException("fsl_ext: mesh file I/O is not provided");
+        loader()(*this, name);
+    }
     // geometry snapshot with the current coordinates (topology shared)
     orc::Mesh synced() const { orc::Mesh o = *m_; o.V.assign(V_.begin(), V_.end()); return o; }
     const orc::Mesh& topo() const { return *m_; }
@@ -475,7 +493,10 @@ inline Point barycentric(const Point& v0, const Point& v1, const Point& v2, cons
 void barycentric_mesh_interpolation(Mesh& up, const Mesh& START, const Mesh& END, int nthreads = 1);
 // A8: metric_resample(in, ref): per-vertex values of `in` resampled at the vertices of `ref` with FSL's ADAPTIVE
 // barycentric kernel, restated in oracle/geom.h (adaptive_barycentric_weights) from the published algorithm it ports.
-Mesh metric_resample(const Mesh& in, const Mesh& ref, int nthreads = 1);
+Mesh metric_resample(const Mesh& in, const Mesh& ref, int nthreads = 1, std::shared_ptr<Mesh> EXCL = nullptr);
+// A9 / A11 (oracle/feat.h): Gaussian smoothing of per-vertex data, exclusion mask from a value band
+Mesh smooth_data(const Mesh& in, const Mesh& ref, double sigma, int nthreads = 1, std::shared_ptr<Mesh> EXCL = nullptr);
+Mesh create_exclusion(const Mesh& data_mesh, float lower, float upper);
 // project_mesh is only reached with anatomical meshes (out of scope): loud if called.
 inline Mesh project_mesh(const Mesh&, const Mesh&, const Mesh&, int = 1) { throw MeshException("fsl_ext: project_mesh is not provided"); }
 

@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "oracle.h"
+#include "feat.h"
 
 using namespace orc;
 
@@ -102,6 +103,61 @@ void orc_metric_resample(const double* in_xyz, int nv_in, const int* in_tris, in
     std::vector<double> v(values, values + (size_t)dims * nv_in);
     const std::vector<double> r = metric_resample(A, v, dims, B);
     std::copy(r.begin(), r.end(), out);
+}
+
+// ---------------- feature pre-processing (oracle/feat.h) ----------------
+void orc_smooth_data(const double* in_xyz, int nv_in, const double* values, int dims, const double* ref_xyz, int nv_ref, double sigma,
+                     const double* mask, double* out) {
+    std::vector<Pt> a(nv_in), b(nv_ref);
+    for (int i = 0; i < nv_in; i++) a[i] = Pt(in_xyz[3 * i], in_xyz[3 * i + 1], in_xyz[3 * i + 2]);
+    for (int i = 0; i < nv_ref; i++) b[i] = Pt(ref_xyz[3 * i], ref_xyz[3 * i + 1], ref_xyz[3 * i + 2]);
+    std::vector<double> v(values, values + (size_t)dims * nv_in);
+    const std::vector<double> r = smooth_data(a, v, dims, b, sigma, mask);
+    std::copy(r.begin(), r.end(), out);
+}
+void orc_histogram_normalization(double* in, int nv_in, const double* ref, int nv_ref, int dims, const double* excl_in, int rows_in,
+                                 const double* excl_ref, int rows_ref) {
+    std::vector<double> a(in, in + (size_t)dims * nv_in), b(ref, ref + (size_t)dims * nv_ref);
+    histogram_normalization(a, nv_in, b, nv_ref, dims, excl_in, rows_in, excl_ref, rows_ref);
+    std::copy(a.begin(), a.end(), in);
+}
+void orc_variance_normalise(double* data, int dims, int nv, const double* mask) {
+    std::vector<double> a(data, data + (size_t)dims * nv);
+    variance_normalise(a, dims, nv, mask);
+    std::copy(a.begin(), a.end(), data);
+}
+void orc_create_exclusion(const double* data, int dims, int nv, float lower, float upper, double* out) {
+    std::vector<double> a(data, data + (size_t)dims * nv);
+    const std::vector<double> m = create_exclusion(a, dims, nv, lower, upper);
+    std::copy(m.begin(), m.end(), out);
+}
+void orc_metric_resample_excl(const double* in_xyz, int nv_in, const int* in_tris, int nf_in, const double* values, int dims, const double* mask,
+                              const double* ref_xyz, int nv_ref, const int* ref_tris, int nf_ref, double* out) {
+    Mesh A = mesh_from(in_xyz, nv_in, in_tris, nf_in), B = mesh_from(ref_xyz, nv_ref, ref_tris, nf_ref);
+    std::vector<double> v(values, values + (size_t)dims * nv_in);
+    const std::vector<double> r = metric_resample_excl(A, v, dims, B, mask);
+    std::copy(r.begin(), r.end(), out);
+}
+// featurespace::initialize for the pairwise driver's two meshes (input, reference).  ico > 0: out_* sized [dims][V(ico)];
+// ico == 0: every mesh keeps its own vertices.  Returns the template's vertex count, -1 on error.
+int orc_featurespace_initialize(int ico, const double* xyz0, int nv0, const int* tris0, int nf0, const double* data0, const double* xyz1, int nv1,
+                                const int* tris1, int nf1, const double* data1, int dims, double sigma0, double sigma1, float thr_lower,
+                                float thr_upper, int intensitynorm, int varnorm, int cut, int exclude, double* out0, double* out1, double* excl0,
+                                double* excl1) {
+    try {
+        std::vector<FeatureMesh> IN(2);
+        IN[0].mesh = mesh_from(xyz0, nv0, tris0, nf0); IN[0].data.assign(data0, data0 + (size_t)dims * nv0); IN[0].D = dims;
+        IN[1].mesh = mesh_from(xyz1, nv1, tris1, nf1); IN[1].data.assign(data1, data1 + (size_t)dims * nv1); IN[1].D = dims;
+        FeatureOptions o;
+        o.sigma = {sigma0, sigma1}; o.thr_lower = thr_lower; o.thr_upper = thr_upper;
+        o.intensitynorm = intensitynorm != 0; o.varnorm = varnorm != 0; o.cut = cut != 0; o.exclude = exclude != 0;
+        std::vector<std::vector<double>> D, E;
+        const Mesh t = featurespace_initialize(ico, IN, o, D, E);
+        std::copy(D[0].begin(), D[0].end(), out0); std::copy(D[1].begin(), D[1].end(), out1);
+        if (excl0 && !E[0].empty()) std::copy(E[0].begin(), E[0].end(), excl0);
+        if (excl1 && !E[1].empty()) std::copy(E[1].begin(), E[1].end(), excl1);
+        return t.nvertices();
+    } catch (const std::exception&) { return -1; }
 }
 
 // ---------------- mesh warp ----------------

@@ -135,6 +135,85 @@ def metric_resample(in_xyz, in_tris, values, ref_xyz, ref_tris):
     return out
 
 
+# ---- feature pre-processing (oracle/feat.h: src/featurespace.cc:18-108, src/reg_tools.cpp:750-810) -----------------------------
+def _mask(m, n):
+    if m is None:
+        return None, None, 0
+    m = np.ascontiguousarray(np.atleast_2d(m), dtype=np.float64)
+    assert m.shape[1] == n
+    return m, m.ctypes.data_as(c_dp), m.shape[0]
+
+
+def smooth_data(in_xyz, values, ref_xyz, sigma, mask=None):
+    """[EXT] A9 newresampler::smooth_data restated: Gaussian of the geodesic distance, support 2 asin(sigma/RAD)."""
+    in_xyz, p1 = _d(in_xyz); values = np.atleast_2d(values); values, p2 = _d(values); ref_xyz, p3 = _d(ref_xyz)
+    m, pm, _ = _mask(mask, len(in_xyz))
+    out = np.empty((values.shape[0], len(ref_xyz)))
+    lib().orc_smooth_data(p1, len(in_xyz), p2, values.shape[0], p3, len(ref_xyz), C.c_double(sigma), pm, out.ctypes.data_as(c_dp))
+    return out
+
+
+def histogram_normalization(data_in, data_ref, excl_in=None, excl_ref=None):
+    """multivariate_histogram_normalization (src/reg_tools.cpp:750-810) over the restated MISCMATHS::Histogram (A10)."""
+    a = np.array(np.atleast_2d(data_in), dtype=np.float64, order="C", copy=True)
+    b, pb_ = _d(np.atleast_2d(data_ref))
+    ea, pea, ra = _mask(excl_in, a.shape[1]); eb, peb, rb = _mask(excl_ref, b.shape[1])
+    lib().orc_histogram_normalization(a.ctypes.data_as(c_dp), a.shape[1], pb_, b.shape[1], a.shape[0], pea, ra, peb, rb)
+    return a
+
+
+def variance_normalise(data, mask=None):
+    """featurespace::variance_normalise (src/featurespace.cc:67-108)."""
+    a = np.array(np.atleast_2d(data), dtype=np.float64, order="C", copy=True)
+    m, pm, _ = _mask(mask, a.shape[1])
+    lib().orc_variance_normalise(a.ctypes.data_as(c_dp), a.shape[0], a.shape[1], pm)
+    return a
+
+
+def create_exclusion(data, lower, upper):
+    """[EXT] A11 newresampler::create_exclusion restated."""
+    a, pa = _d(np.atleast_2d(data))
+    out = np.empty(a.shape[1])
+    lib().orc_create_exclusion(pa, a.shape[0], a.shape[1], C.c_float(lower), C.c_float(upper), out.ctypes.data_as(c_dp))
+    return out
+
+
+def metric_resample_excl(in_xyz, in_tris, values, mask, ref_xyz, ref_tris):
+    in_xyz, p1 = _d(in_xyz); in_tris, p2 = _i(in_tris); values = np.atleast_2d(values); values, p3 = _d(values)
+    ref_xyz, p4 = _d(ref_xyz); ref_tris, p5 = _i(ref_tris)
+    m, pm, _ = _mask(mask, len(in_xyz))
+    out = np.empty((values.shape[0], len(ref_xyz)))
+    lib().orc_metric_resample_excl(p1, len(in_xyz), p2, len(in_tris), p3, values.shape[0], pm, p4, len(ref_xyz), p5, len(ref_tris),
+                                   out.ctypes.data_as(c_dp))
+    return out
+
+
+def featurespace_initialize(ico, mesh_in, data_in, mesh_ref, data_ref, sigma=(5.0, 5.0), thresholds=(0.0, 0.0), intensitynorm=False,
+                            varnorm=False, cut=False, exclude=False):
+    """featurespace::initialize (src/featurespace.cc:18-65) for the pairwise driver's (input, reference) pair.
+    mesh_* = (xyz, tris); data_* = [D][V].  Returns (DATA[0], DATA[1], EXCL[0] or None, EXCL[1] or None)."""
+    x0, p0 = _d(mesh_in[0]); t0, q0 = _i(mesh_in[1]); x1, p1 = _d(mesh_ref[0]); t1, q1 = _i(mesh_ref[1])
+    d0 = np.atleast_2d(data_in); d0, pd0 = _d(d0); d1 = np.atleast_2d(data_ref); d1, pd1 = _d(d1)
+    D = d0.shape[0]
+    if ico > 0:
+        nv, nf = C.c_int(), C.c_int()
+        lib().orc_icosphere_counts(ico, C.byref(nv), C.byref(nf))
+        v0 = v1 = nv.value
+    else:
+        v0, v1 = len(x0), len(x1)
+    o0, o1 = np.empty((D, v0)), np.empty((D, v1))
+    e0, e1 = np.full(len(x0), np.nan), np.full(len(x1), np.nan)
+    lib().orc_featurespace_initialize.restype = C.c_int
+    rc = lib().orc_featurespace_initialize(int(ico), p0, len(x0), q0, len(t0), pd0, p1, len(x1), q1, len(t1), pd1, D, C.c_double(sigma[0]),
+                                           C.c_double(sigma[1]), C.c_float(thresholds[0]), C.c_float(thresholds[1]), int(intensitynorm),
+                                           int(varnorm), int(cut), int(exclude), o0.ctypes.data_as(c_dp), o1.ctypes.data_as(c_dp),
+                                           e0.ctypes.data_as(c_dp), e1.ctypes.data_as(c_dp))
+    if rc < 0:
+        raise RuntimeError("featurespace_initialize failed")
+    has = exclude or cut
+    return o0, o1, (e0 if has else None), (e1 if has else None)
+
+
 def mesh_interpolate(pts, from_xyz, tris, to_xyz):
     """[EXT] barycentric_mesh_interpolation(SPH_up, SPH_low_init, SPH_low_final) restated (src/mesh_registration.cpp:390)."""
     pts, pp = _d(pts); from_xyz, pf = _d(from_xyz); tris, pt = _i(tris); to_xyz, po = _d(to_xyz)
