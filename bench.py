@@ -628,6 +628,9 @@ def main():
                     help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
                          "and triplets sharded over the GPUs (strong scaling); group: groupwise registration "
                          "(DiscreteGroupCostFunction triplet costs of --group-subjects subjects, subjects sharded over the GPUs)")
+    ap.add_argument("--resident-streams", type=int, default=4,
+                    help="streams the subjects of one GPU are spread over in the resident (device-timed) step: independent registrations "
+                         "overlap on the device, fork/join by events around the timed region (1 = everything on one stream)")
     ap.add_argument("--level-wall", type=int, default=1,
                     help="1: also time one resolution level end to end (one outer iteration; N = 1 only; needs oracle/_ref for the "
                          "reference's optimiser); 0: skip")
@@ -707,11 +710,16 @@ def main():
     cxyz0, ctris = host.icosphere(args.cp_level)
     edge = np.linalg.norm(cxyz0[ctris[:, 0]] - cxyz0[ctris[:, 1]], axis=1)
     mvd = float(edge.mean())
-    # one explicit (non-default) stream for every context: the events below are recorded on the SAME stream the kernels
-    # are launched on (a NULL stream handle would make each context fall back to its own private stream)
+    # Explicit (non-default) streams.  `stream` is the timing stream: the events below are recorded on it.  The subjects of this
+    # GPU are independent registrations and are spread round-robin over `work_streams`, so that the small latency-bound kernels
+    # of one subject (voxel grid, per-control-point set-up) overlap the big ones of another; every timed region forks from
+    # `stream` (each work stream waits for the start event) and joins back into it (it waits for every work stream's end event)
+    # before the stop event is recorded — all on the device.
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+    n_streams = max(1, min(args.resident_streams, args.subjects_per_gpu))
+    work_streams = [stream] if n_streams == 1 else [torch.cuda.Stream() for _ in range(n_streams)]
     models, ctxs, subs, host_bufs = [], [], [], []
     for s in range(B):
         seed = 1000 + 97 * rank + s
@@ -724,7 +732,7 @@ def main():
         m.reset_cpgrid(cxyz)
         m.setup()
         c = m.context()
-        c.set_stream(stream.cuda_stream)
+        c.set_stream(work_streams[s % n_streams].cuda_stream)
         models.append(m); ctxs.append(c); subs.append(S)
         host_bufs.append((torch.from_numpy(S.sxyz.copy()).pin_memory(), torch.from_numpy(cxyz.copy()).pin_memory()))
     N, L, T = models[0].N, models[0].L, models[0].T
@@ -767,11 +775,20 @@ def main():
             torch.cuda.synchronize()
 
     def timed(fn, steps):
+        nonlocal n_streams
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
         e0.record(stream)
+        if n_streams > 1:
+            for ws in work_streams:
+                ws.wait_event(e0)                 # fork
         for _ in range(steps):
             fn()
+        if n_streams > 1:
+            for ws in work_streams:
+                j = torch.cuda.Event()
+                j.record(ws)
+                stream.wait_event(j)              # join
         e1.record(stream)
         sync_all()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -784,14 +801,25 @@ def main():
     sync_all()
     ms_tables_only = timed(lambda: resident_step(False), args.steps)      # secondary: tables only (no patch construction)
     launches0 = sum(c.launch_count() for c in ctxs)
-    for c in ctxs:
-        c.set_timing(2)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     ms_per_step = timed(resident_step, args.steps)                          # headline: patches + unary table + fusion moves
     launches = sum(c.launch_count() for c in ctxs) - launches0
+    # Per-kernel durations (the roofline's denominator) are only meaningful when kernels of different subjects do not share the
+    # device: a second timed region of the SAME step with every subject on the timing stream, event pairs around each family
+    ms_single_stream = ms_per_step
+    if n_streams > 1:
+        for c in ctxs:
+            c.set_stream(stream.cuda_stream)
+        n_streams_saved, n_streams = n_streams, 1
+        resident_step()
+    for c in ctxs:
+        c.set_timing(2)
+    ms_timed_kernels = timed(resident_step, args.steps)
+    if args.resident_streams > 1 and B > 1:
+        ms_single_stream = ms_timed_kernels
     fam = {}
     for c in ctxs:
         for f in ("unary_main", "triplet_moves", "patches", "unary"):
@@ -904,7 +932,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "subjects_per_gpu": B, "N": N, "L": L, "T": T, "mean_patch": float(np.mean(patch_totals)) / N,
                        "evals_per_subject": evals_per_subject, "l2": "working set of B subjects per GPU exceeds the 126 MB L2 (no flush needed)",
-                       "parallelism": f"subjects x{world} (no data-path collective)"},
+                       "parallelism": f"subjects x{world} (no data-path collective)",
+                       "resident_streams": max(1, min(args.resident_streams, B))},
             "roofline": {"bound": "hbm", "kernel": "k_unary", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_l2": l2_traffic,
                          "traffic_l1_global_loads": l1_traffic, "peak_source": peak_src,
@@ -915,6 +944,7 @@ def main():
                     "api": "NonLinearSRegDiscreteModel::reset_meshspace/reset_CPgrid/setupCostFunction + computeTripletMoves"},
             "gpu_launches": int(launches), "clocks": clocks,
             "value_tables_only": value_tables_only, "ms_per_step_tables_only": ms_tables_only,
+            "ms_per_step_one_stream": ms_single_stream,
             "step": "per subject: get_source_data (patch construction, one-pass path) + whole unary table + all-label fusion-move triplet costs",
             "kernel_ms_per_subject": {f: (v[0] / v[1] if v[1] else None) for f, v in fam.items()},
             "patch_builds_one_pass_vs_exact": [sum(x[0] for x in one_pass), sum(x[1] for x in one_pass)],

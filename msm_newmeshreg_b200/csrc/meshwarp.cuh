@@ -45,7 +45,10 @@ __device__ __forceinline__ double w_cone_margin(const WarpArgs& a, int t, const 
     double A[3], B[3], C[3];
     w_unit(a.from + 3 * a.tris[3 * t], A); w_unit(a.from + 3 * a.tris[3 * t + 1], B); w_unit(a.from + 3 * a.tris[3 * t + 2], C);
     if (u[0] * (A[0] + B[0] + C[0]) + u[1] * (A[1] + B[1] + C[1]) + u[2] * (A[2] + B[2] + C[2]) <= 0.0) return -1e300;
-    return fmin(w_triple(u, A, B), fmin(w_triple(u, B, C), w_triple(u, C, A)));
+    // either winding: inside the cone the three edge-plane tests have the sign of A . (B x C)
+    const double sg = w_triple(A, B, C) < 0.0 ? -1.0 : 1.0;
+    return sg * (sg > 0.0 ? fmin(w_triple(u, A, B), fmin(w_triple(u, B, C), w_triple(u, C, A)))
+                          : fmax(w_triple(u, A, B), fmax(w_triple(u, B, C), w_triple(u, C, A))));
 }
 __device__ __forceinline__ double w_area(const double* a, const double* b, const double* c) {
     const double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};

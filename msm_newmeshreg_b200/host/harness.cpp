@@ -10,6 +10,7 @@
 //     `refcost`) — the CPU reference the GPU path and the oracle port are pinned against.
 #include <cstring>
 #include <memory>
+#include <random>
 
 #ifdef WITH_REF_COST
 #include "DiscreteGroupModel.h"  // /root/reference/src (the product mirror is NOT on the include path of this build)
@@ -27,6 +28,36 @@
 #ifndef WITH_REF_COST
 #include "src/FusionTables.h"
 #endif
+#endif
+
+#ifdef WITH_REF_DRIVER_LOOP
+// The reference's driver loop and MCMC optimiser, textually (oracle/Makefile cuts Mesh_registration::run_discrete_opt out of
+// src/mesh_registration.cpp into oracle/_ref/gen/ at build time; src/mcmc_opt.h is included where it lies).  In the product
+// build the reference header's include guard is pre-defined, so that its `#include "DiscreteModel.h"` (which would find the
+// reference's own file next to it) is a no-op and MCMC::optimise compiles against the mirror classes declared above.
+#ifndef WITH_REF_COST
+#define NEWMESHREG_DISCRETEMODEL_H
+#endif
+#include REF_MCMC_H
+namespace newmeshreg {
+// Exactly the members Mesh_registration::run_discrete_opt reads (src/mesh_registration.h:52-57,88-91,107-108,111-112,128,
+// 135-136,146,155), with their types; everything else of the driver class is option parsing and file I/O.
+class Mesh_registration {
+public:
+    int level = 1;
+    std::shared_ptr<NonLinearSRegDiscreteModel> model;
+    NEWMAT::Matrix SPHin_CFWEIGHTING, SPHref_CFWEIGHTING;
+    std::string _discreteOPT;
+    myparam PARAMETERS;
+    bool _tricliquelikeihood = false, _incfw = false, _refcfw = false;
+    std::vector<int> _mciters;
+    int _numthreads = 1;
+    bool _verbose = false;
+    NEWMAT::Matrix combine_costfunction_weighting(const NEWMAT::Matrix&, const NEWMAT::Matrix&);
+    void run_discrete_opt(newresampler::Mesh&);
+};
+#include "_ref/gen/run_discrete_opt.inc"
+}  // namespace newmeshreg
 #endif
 
 using namespace newmeshreg;
@@ -800,6 +831,30 @@ int ref_run_discrete_opt(void* h, int iters, int threads, double* source_xyz, in
     });
     return st == 0 ? done : -1;
 }
+#ifdef WITH_REF_DRIVER_LOOP
+// Mesh_registration::run_discrete_opt ITSELF (the text of src/mesh_registration.cpp:316-397, see the top of this file) on this
+// box's model: `iters` outer iterations, optimiser = the model's dOPT ("HOCR" / "FastPD" / "MCMC" with mciters sweeps), unit
+// cost-function weighting.  source_xyz is updated in place; cpgrid_out / labeling_out (optional) = the model's final state.
+int ref_driver_run_discrete_opt(void* h, int iters, int threads, int mciters, double* source_xyz, double* cpgrid_out, int* labeling_out) {
+    auto* b = (ModelBox*)h;
+    return guard([&] {
+        Mesh_registration reg;
+        reg.model = b->model;
+        reg.PARAMETERS = b->params;
+        reg.PARAMETERS["iters"] = iters;
+        reg._discreteOPT = boost::get<std::string>(b->params.find("dOPT")->second);
+        reg._numthreads = threads;
+        reg._mciters = {mciters};
+        newresampler::Mesh source = b->source;
+        assign_coords(source, source_xyz);
+        reg.run_discrete_opt(source);
+        auto c = coords_of(source);
+        std::memcpy(source_xyz, c.data(), c.size() * sizeof(double));
+        if (cpgrid_out) { auto g = coords_of(b->model->get_CPgrid()); std::memcpy(cpgrid_out, g.data(), g.size() * sizeof(double)); }
+        if (labeling_out) std::memcpy(labeling_out, b->model->getLabeling(), sizeof(int) * b->model->getNumNodes());
+    });
+}
+#endif
 // src/mesh_registration.cpp:346-352
 int ref_fastpd_model(void* h, double* energy) {
     auto* b = (ModelBox*)h;

@@ -143,6 +143,19 @@ inline std::vector<double> metric_resample(const Mesh& in, const double* values,
     return out;
 }
 
+// The reference's own signature (src/mesh_registration.cpp:326, src/DiscreteGroupModel.cpp:92): values travel as the meshes'
+// pvalues ([dims][V]); returns `ref` carrying the resampled rows.
+inline Mesh metric_resample(const Mesh& in, const Mesh& ref, int /*nthreads*/ = 1) {
+    const NEWMAT::Matrix pv = in.get_pvalues();
+    if (pv.Ncols() != in.nvertices()) throw newmeshreg::MeshregException("metric_resample: per-vertex values do not match the mesh");
+    const std::vector<double> r = metric_resample(in, pv.data(), pv.Nrows(), ref);
+    NEWMAT::Matrix out(pv.Nrows(), ref.nvertices());
+    std::copy(r.begin(), r.end(), out.data());
+    Mesh o = ref;
+    o.set_pvalues(out);
+    return o;
+}
+
 // metric_resample(in, ref, threads, EXCL) with an exclusion mask over the `in` vertices (src/featurespace.cc:46): excluded sources
 // (mask <= 0) drop out of every weight list, the rest is renormalised, a vertex left without sources gets 0.  mask == nullptr:
 // the plain call above.

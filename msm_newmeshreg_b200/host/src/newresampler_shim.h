@@ -166,6 +166,13 @@ public:
         for (int t = 0; t < ntriangles(); t++) a[t] = get_triangle(t).get_angles();
         return a;
     }
+    // per-vertex values ("pvalues", one row per dimension): carried for the driver's cost-function weighting
+    // (src/mesh_registration.cpp:323-327); shared between copies until one side sets new ones
+    void set_pvalues(const NEWMAT::Matrix& M) { pv_ = std::make_shared<NEWMAT::Matrix>(M); }
+    NEWMAT::Matrix get_pvalues() const { return pv_ ? *pv_ : NEWMAT::Matrix(); }
+    int npvalues() const { return pv_ ? pv_->Ncols() : 0; }
+    int get_dimension() const { return pv_ ? pv_->Nrows() : 0; }
+    double get_pvalue(int i, int dim = 0) const { return (*pv_)(dim + 1, i + 1); }
     // construction
     void set(const double* xyz, int nv, const int* tris, int nf, int resolution = -1) {
         topo_ = std::make_shared<Topo>();  // never mutate a topology another copy may share
@@ -216,6 +223,7 @@ private:
         std::vector<std::vector<int>> nbr, vtri;
     };
     std::shared_ptr<Topo> topo_ = std::make_shared<Topo>();
+    std::shared_ptr<NEWMAT::Matrix> pv_;
     int resolution_ = -1;
 };
 

@@ -131,6 +131,22 @@ def fusion_model(m, threads=1):
     return m.labeling(), e.value
 
 
+def driver_run_discrete_opt(m, source_xyz, iters, threads=1, mciters=0):
+    """Mesh_registration::run_discrete_opt ITSELF — the text of src/mesh_registration.cpp:316-397, cut out at build time and
+    compiled unmodified (oracle/Makefile, host/harness.cpp WITH_REF_DRIVER_LOOP) — over the reference's own classes, all on the CPU.
+    Returns (warped source, final control grid, final labelling)."""
+    src = np.array(source_xyz, dtype=np.float64, order="C", copy=True)
+    grid = np.zeros((m.N, 3)); lab = np.zeros(m.N, np.int32)
+    if lib().ref_driver_run_discrete_opt(m.h, int(iters), int(threads), int(mciters), src.ctypes.data_as(c_dp), grid.ctypes.data_as(c_dp),
+                                         lab.ctypes.data_as(c_ip)) != 0:
+        raise RuntimeError(lib().msmhost_last_error().decode())
+    return src, grid, lab
+
+
+def has_driver_loop():
+    return hasattr(lib(), "ref_driver_run_discrete_opt")
+
+
 def run_discrete_opt(m, source_xyz, iters, threads=1):
     """Mesh_registration::run_discrete_opt (src/mesh_registration.cpp:316-397) — reference cost functions AND reference
     optimisers, all on the CPU.  Same return convention as oracle.pyref.run_discrete_opt."""

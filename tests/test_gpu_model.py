@@ -200,6 +200,59 @@ def test_run_discrete_opt_gpu_equals_reference_end_to_end(built, dopt, rmode):
     g.close(); r.close()
 
 
+@pytest.mark.skipif(not (_have_refcost() and pyref.available()), reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("dopt,rmode", [("HOCR", 3), ("FastPD", 1)])
+def test_the_references_own_driver_loop_runs_unchanged_over_the_mirror(built, dopt, rmode):
+    """Drop-in at source level: the TEXT of Mesh_registration::run_discrete_opt (src/mesh_registration.cpp:316-397; cut out at
+    build time, oracle/Makefile) compiled unmodified against the product's mirror classes drives the GPU, and — compiled against
+    the reference's own classes — is the reference.  Same labelling, control grid and warped source after three iterations."""
+    from msm_newmeshreg_b200 import host
+    from oracle import pyrefcost
+    if not (pyref.has_driver_loop() and pyrefcost.has_driver_loop()):
+        pytest.skip("oracle/_ref built without the driver loop")
+    P = pb.make_problem(4, 2, 1, seed=73, warp=0.0)
+    pr = dict(pb.DEFAULT_PARAMS); pr.update(rmode=rmode, dopt=dopt)
+    g = host.Model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, _lib_override=pyref.lib(), **pr)
+    r = pyrefcost.model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, threads=1, **pr)
+    for m in (g, r):
+        m.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref); m.initialize()
+    start = pb.smooth_warp(P.txyz, 173, 0.2 * P.mvd)
+    sg, gg, lg = pyref.driver_run_discrete_opt(g, start, 3, threads=4)
+    sr, gr, lr = pyrefcost.driver_run_discrete_opt(r, start, 3, threads=1)
+    sing = pb.singular_nodes(P)
+    keep = np.ones(P.N, bool); keep[sing] = False
+    assert np.array_equal(lg[keep], lr[keep])
+    assert np.abs(gg - gr)[keep].max() < 1e-4
+    d_sing = np.linalg.norm(P.txyz - P.cxyz0[sing[0]], axis=1) if len(sing) else np.full(len(P.txyz), 1e9)
+    assert np.abs(sg - sr)[d_sing > 2.5 * P.mvdmax].max() < 1e-4
+    # and it is the loop the harness restates (tests above): same warped source
+    g2 = host.Model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, _lib_override=pyref.lib(), **pr)
+    g2.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref); g2.initialize()
+    s2, _, _, _ = pyref.run_discrete_opt(g2, start, 3, threads=4)
+    assert np.abs(s2 - sg).max() < 1e-9
+    g.close(); r.close(); g2.close()
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+def test_the_references_mcmc_optimiser_runs_over_the_mirror(built):
+    """MCMC::optimise (src/mcmc_opt.h, included where it lies) compiled against the mirror: reads the GPU-built unary table and
+    the re-entrant triplet virtual.  Randomised (std::random_device): only the energy contract is checked — it never accepts
+    a move that raises unary + triplet of the clique it looks at, so the total stays finite and the labelling valid."""
+    from msm_newmeshreg_b200 import host
+    if not pyref.has_driver_loop():
+        pytest.skip("oracle/_ref built without the driver loop")
+    P = pb.make_problem(4, 2, 1, seed=74, warp=0.0)
+    pr = dict(pb.DEFAULT_PARAMS); pr.update(rmode=3, dopt="MCMC")
+    g = host.Model(sgres=P.cp_level + 2, cpres=P.cp_level, multivariate=False, _lib_override=pyref.lib(), **pr)
+    g.set_data(P.txyz, P.ttris, P.txyz, P.ttris, P.inp, P.ref); g.initialize()
+    start = pb.smooth_warp(P.txyz, 174, 0.2 * P.mvd)
+    s, grid, lab = pyref.driver_run_discrete_opt(g, start, 1, threads=2, mciters=20)
+    assert np.isfinite(s).all() and np.isfinite(grid).all()
+    assert lab.min() >= 0 and lab.max() < g.L and (lab != 0).any()
+    assert np.abs(np.linalg.norm(s, axis=1) - 100.0).max() < 1e-6
+    g.close()
+
+
 def test_triplet_moves_fp32_variant_is_the_rounded_fp64_table(built):
     P = pb.make_problem(4, 2, 1, seed=81, warp=0.3, deform_cp=0.1)
     m = _model(P, rmode=3); m.reset_cpgrid(P.cxyz); m.setup()

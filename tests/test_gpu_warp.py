@@ -61,6 +61,29 @@ def test_mesh_interpolate_parity(built, cp_level, deform):
 
 
 @pytest.mark.gpu
+def test_mesh_interpolate_accepts_either_winding(built):
+    """msm_mesh_interpolate promises "any closed spherical triangle mesh": faces wound inward (two corners swapped) locate the
+    same triangles and give the same result as the outward-wound mesh."""
+    from msm_newmeshreg_b200 import Context
+    cxyz0, ctris = pyorc.icosphere(3)
+    _, _, mvd = pyorc.spacings(cxyz0, ctris)
+    start = pb.smooth_warp(cxyz0, 3, 0.2 * mvd)
+    end = pb.smooth_warp(cxyz0, 4, 0.4 * mvd)
+    pts, _ = pyorc.icosphere(4)
+    pts = pb.smooth_warp(pts, 5, 0.5)
+    ctx = Context()
+    out, tri, w = ctx.mesh_interpolate(pts, start, ctris, end, details=True)
+    flipped = ctris[:, [0, 2, 1]].copy()
+    mixed = ctris.copy(); mixed[::2] = flipped[::2]
+    for faces in (flipped, mixed):
+        o2, t2, w2 = ctx.mesh_interpolate(pts, start, faces, end, details=True)
+        interior = w.min(1) > 1e-9
+        assert np.array_equal(t2[interior], tri[interior])
+        assert np.abs(o2 - out).max() < 1e-9
+    ctx.close()
+
+
+@pytest.mark.gpu
 def test_host_warp_functions(built):
     from msm_newmeshreg_b200 import host
     cxyz0, ctris = pyorc.icosphere(3)

@@ -246,3 +246,19 @@ def test_hierarchy_builder_rejects_what_is_not_a_regular_icosphere(ich):
     bad = tris.copy(); bad[5] = bad[6]                         # a face twice, another missing
     assert _ich_build(ich, xyz, bad) != 0
     assert _ich_build(ich, xyz * np.array([1.0, 1.0, 1.02]), tris) != 0 and re.search(b"sphere", ich.ich_error())
+
+
+def test_reference_driver_loop_compiles_against_the_mirror():
+    """Compile-level drop-in proof (no GPU needed): oracle/_ref/libref_optim.so is host/harness.cpp built over the MIRROR headers
+    together with the unmodified text of Mesh_registration::run_discrete_opt / combine_costfunction_weighting
+    (src/mesh_registration.cpp:316-397,888-909), src/mcmc_opt.h and the vendored Fusion / FastPD / ELC headers — if any name,
+    signature or type of the mirror's model surface drifted from the reference's, that library would not build."""
+    import ctypes
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_optim.so")
+    if not os.path.exists(so):
+        import pytest
+        pytest.skip("oracle/_ref/libref_optim.so not built (needs /root/reference at build time)")
+    lib = ctypes.CDLL(so)
+    for name in ("ref_driver_run_discrete_opt", "ref_run_discrete_opt", "ref_fusion_model", "ref_fastpd_model", "msmhost_featurespace_initialize"):
+        assert hasattr(lib, name), name
