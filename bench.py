@@ -628,7 +628,7 @@ def main():
                     help="subjects: B independent subjects per GPU (weak scaling, default); cp: ONE subject, control points "
                          "and triplets sharded over the GPUs (strong scaling); group: groupwise registration "
                          "(DiscreteGroupCostFunction triplet costs of --group-subjects subjects, subjects sharded over the GPUs)")
-    ap.add_argument("--resident-streams", type=int, default=4,
+    ap.add_argument("--resident-streams", type=int, default=8,
                     help="streams the subjects of one GPU are spread over in the resident (device-timed) step: independent registrations "
                          "overlap on the device, fork/join by events around the timed region (1 = everything on one stream)")
     ap.add_argument("--level-wall", type=int, default=1,

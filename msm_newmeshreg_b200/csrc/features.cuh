@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(128) k_smooth(SmoothArgs a) {
     const int y0 = bin_coord(g, cy - a.chord_max), y1 = bin_coord(g, cy + a.chord_max);
     const int z0 = bin_coord(g, cz - a.chord_max), z1 = bin_coord(g, cz + a.chord_max);
     const double inv2s2 = 1.0 / (2.0 * a.sigma * a.sigma);
+    const double c2_reject = a.chord_max * a.chord_max * (1.0 + 1e-12);
     for (int d0 = 0; d0 < a.D; d0 += DB) {
         double W = 0.0, acc[DB];
 #pragma unroll
@@ -62,8 +63,10 @@ __global__ void __launch_bounds__(128) k_smooth(SmoothArgs a) {
                     const int j = g.sorted[s];
                     if (a.mask && !(a.mask[j] > 0.0)) continue;
                     const double ex = cx - a.in_xyz[3 * j], ey = cy - a.in_xyz[3 * j + 1], ez = cz - a.in_xyz[3 * j + 2];
-                    const double chord = sqrt(ex * ex + ey * ey + ez * ez);
-                    if (!(chord < a.chord_max)) continue;
+                    const double d2 = ex * ex + ey * ey + ez * ez;
+                    if (d2 > c2_reject) continue;                         // most candidates of the 27 cells: no sqrt / asin / exp
+                    const double chord = sqrt(d2);
+                    if (!(chord < a.chord_max)) continue;                 // the decision itself, as the reference's restatement makes it
                     const double d = 2.0 * RAD * asin(fmin(1.0, chord / (2.0 * RAD)));
                     const double w = exp(-(d * d) * inv2s2);
                     W += w;

@@ -248,7 +248,7 @@ def test_the_references_mcmc_optimiser_runs_over_the_mirror(built):
     start = pb.smooth_warp(P.txyz, 174, 0.2 * P.mvd)
     s, grid, lab = pyref.driver_run_discrete_opt(g, start, 1, threads=2, mciters=20)
     assert np.isfinite(s).all() and np.isfinite(grid).all()
-    assert lab.min() >= 0 and lab.max() < g.L and (lab != 0).any()
+    assert lab.min() >= 0 and lab.max() < len(P.labels) and (lab != 0).any()
     assert np.abs(np.linalg.norm(s, axis=1) - 100.0).max() < 1e-6
     g.close()
 
