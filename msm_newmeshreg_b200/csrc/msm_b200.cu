@@ -1079,6 +1079,8 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
         s.tref = ctx->d_tref.as<float>();
         s.face_feat = CQ == 0 ? ctx->d_face_feat.as<float>() : nullptr;
         s.pcx = ctx->d_pcx.as<float>(); s.pcy = ctx->d_pcy.as<float>(); s.pcz = ctx->d_pcz.as<float>();
+        k_cp_hint<<<(Ns + 127) / 128, 128, 0, ctx->stream>>>(s, Ns);
+        KLAUNCH_CHECK();
         k_unary_setup<<<(Ns + 3) / 4, 128, 0, ctx->stream>>>(s, Ns);
         KLAUNCH_CHECK();
     }

@@ -1,7 +1,7 @@
 // unary.cuh — the unary data term (src/DiscreteCostFunction.cpp:306-313,412-448,483-526; similarities.cc:122-173).
 //
-// k_unary_setup (fp64, one warp per control point k): the level-h "hint" face under CP_k, CP_k's corner coordinates in
-//   it, and from those
+// k_cp_hint (fp64, one thread per control point k): the level-h "hint" face under CP_k (and the target value under CP_k);
+// k_unary_setup (fp64, one warp per control point k): CP_k's corner coordinates in that face, and from those
 //     per sample i :  c_i = x(CP_k) + A r_i           (r_i = SRC_i - CP_k, the packed offsets)
 //     per label  l :  M_l = A (R_kl - I),  g_l = A (R_kl - I) CP_k
 //   where A is the dual basis of the hint face (x = A p are the coordinates of p in the face's corner basis); plus
@@ -68,8 +68,36 @@ struct UnarySetupArgs {
     float* pcx; float* pcy; float* pcz; // [total] corner coordinates of the unrotated samples
 };
 
-// One WARP per control point (4 per CTA, no block barrier): lane 0 walks the fp64 hierarchy — hint face, then on to the
-// leaf for the reference target value — the other lanes then form, from the hint face's dual basis A,
+// One THREAD per control point: the fp64 walk down the hierarchy — hint face, then on to the leaf for the reference target
+// value.  A chain of dependent table reads per control point, so control points go side by side (it used to be lane 0 of the
+// warp below, 31 lanes waiting).
+__global__ void __launch_bounds__(128) k_cp_hint(UnarySetupArgs a, int Ns) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= Ns) return;
+    const int k = a.k_begin + row;
+    int base, n; double al, be, ga;
+    descend_d(a.ico, a.hint.h, a.cp[3 * k], a.cp[3 * k + 1], a.cp[3 * k + 2], base, n, al, be, ga);
+    a.hint_face[row] = base * a.hint.nf_per_base + (n - a.hint.node_off);
+    float tr = 0.f;
+    if (a.face_feat) {  // continue the same descent down to the leaf
+        for (int l = a.hint.h; l < a.ico.depth; l++) {
+            const double4 nn = a.ico.ntab_d[n];
+            const double s = al + be + ga;
+            const double sa = (al + al) - s, sb = (be + be) - s, sc = (ga + ga) - s;
+            int child; double x, y, z;
+            if (sa > 0.0) { child = 0; x = sa; y = be * nn.x; z = ga * nn.z; }
+            else if (sb > 0.0) { child = 1; x = al * nn.x; y = sb; z = ga * nn.y; }
+            else if (sc > 0.0) { child = 2; x = al * nn.z; y = be * nn.y; z = sc; }
+            else { child = 3; x = -sa * nn.y; y = -sb * nn.z; z = -sc * nn.x; }
+            al = x; be = y; ga = z;
+            n = 4 * n + 1 + child;
+        }
+        tr = reinterpret_cast<const float4*>(a.face_feat)[base * a.ico.nleaf_per_base + (n - a.ico.leaf_off)].x;
+    }
+    a.tref[row] = tr;
+}
+
+// One WARP per control point (4 per CTA, no block barrier): from the hint face's dual basis A (k_cp_hint found the face),
 //     per sample i :  c_i = A CP_k + A r_i     and     per label l :  M_l = A K_kl,  g_l = A K_kl CP_k.
 __global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
     const int lane = threadIdx.x & 31;
@@ -77,31 +105,7 @@ __global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
     if (row >= Ns) return;   // whole warps leave together
     const int k = a.k_begin + row;
     const double ox = a.cp[3 * k], oy = a.cp[3 * k + 1], oz = a.cp[3 * k + 2];
-    int f = 0;
-    if (lane == 0) {
-        int base, n; double al, be, ga;
-        descend_d(a.ico, a.hint.h, ox, oy, oz, base, n, al, be, ga);
-        f = base * a.hint.nf_per_base + (n - a.hint.node_off);
-        a.hint_face[row] = f;
-        float tr = 0.f;
-        if (a.face_feat) {  // continue the same descent down to the leaf
-            for (int l = a.hint.h; l < a.ico.depth; l++) {
-                const double4 nn = a.ico.ntab_d[n];
-                const double s = al + be + ga;
-                const double sa = (al + al) - s, sb = (be + be) - s, sc = (ga + ga) - s;
-                int child; double x, y, z;
-                if (sa > 0.0) { child = 0; x = sa; y = be * nn.x; z = ga * nn.z; }
-                else if (sb > 0.0) { child = 1; x = al * nn.x; y = sb; z = ga * nn.y; }
-                else if (sc > 0.0) { child = 2; x = al * nn.z; y = be * nn.y; z = sc; }
-                else { child = 3; x = -sa * nn.y; y = -sb * nn.z; z = -sc * nn.x; }
-                al = x; be = y; ga = z;
-                n = 4 * n + 1 + child;
-            }
-            tr = reinterpret_cast<const float4*>(a.face_feat)[base * a.ico.nleaf_per_base + (n - a.ico.leaf_off)].x;
-        }
-        a.tref[row] = tr;
-    }
-    f = __shfl_sync(0xffffffffu, f, 0);
+    const int f = a.hint_face[row];
     double A[9];   // same address in every lane: one broadcast transaction each
 #pragma unroll
     for (int j = 0; j < 9; j++) A[j] = a.hint.hdual[(size_t)f * 9 + j];
