@@ -28,6 +28,7 @@ struct WarpArgs {
     const int* tris;       // [F][3]
     WarpGrid grid;
     double radius;         // output radius (RAD)
+    double orient;         // +1: faces wound outward, -1: inward (the mesh's OVERALL orientation, decided once on the host)
     double* out;           // [M][3]
     int* tri_out;          // optional [M]
     double* w_out;         // optional [M][3]
@@ -45,10 +46,9 @@ __device__ __forceinline__ double w_cone_margin(const WarpArgs& a, int t, const 
     double A[3], B[3], C[3];
     w_unit(a.from + 3 * a.tris[3 * t], A); w_unit(a.from + 3 * a.tris[3 * t + 1], B); w_unit(a.from + 3 * a.tris[3 * t + 2], C);
     if (u[0] * (A[0] + B[0] + C[0]) + u[1] * (A[1] + B[1] + C[1]) + u[2] * (A[2] + B[2] + C[2]) <= 0.0) return -1e300;
-    // either winding: inside the cone the three edge-plane tests have the sign of A . (B x C)
-    const double sg = w_triple(A, B, C) < 0.0 ? -1.0 : 1.0;
-    return sg * (sg > 0.0 ? fmin(w_triple(u, A, B), fmin(w_triple(u, B, C), w_triple(u, C, A)))
-                          : fmax(w_triple(u, A, B), fmax(w_triple(u, B, C), w_triple(u, C, A))));
+    // a.orient = -1 for a mesh whose faces are wound inward as a whole; a single flipped face of a folded mesh keeps a negative
+    // margin either way (it does not contain points the way its neighbours do: oracle/geom.h SphereLocator)
+    return fmin(a.orient * w_triple(u, A, B), fmin(a.orient * w_triple(u, B, C), a.orient * w_triple(u, C, A)));
 }
 __device__ __forceinline__ double w_area(const double* a, const double* b, const double* c) {
     const double e1[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, e2[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};

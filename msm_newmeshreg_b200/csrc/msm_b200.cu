@@ -1452,14 +1452,18 @@ int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* f
         if (!(n > 0)) FAIL("msm_mesh_interpolate: vertex at the origin");
         for (int d = 0; d < 3; d++) u[3 * i + d] = from_xyz[3 * i + d] / n;
     }
-    double mean_edge = 0;
+    double mean_edge = 0, signed_volume = 0;
     for (int t = 0; t < F; t++) {
         for (int j = 0; j < 3; j++)
             if (tris[3 * t + j] < 0 || tris[3 * t + j] >= V) FAIL("msm_mesh_interpolate: triangle index out of range");
-        const double* a = &u[3 * tris[3 * t]]; const double* b = &u[3 * tris[3 * t + 1]];
+        const double* a = &u[3 * tris[3 * t]]; const double* b = &u[3 * tris[3 * t + 1]]; const double* c = &u[3 * tris[3 * t + 2]];
         mean_edge += std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+        signed_volume += a[0] * (b[1] * c[2] - b[2] * c[1]) + a[1] * (b[2] * c[0] - b[0] * c[2]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
     }
     mean_edge /= F;
+    // overall orientation of the mesh: faces wound inward as a whole (negative enclosed volume) are read the other way round;
+    // single flipped faces of a folded mesh do not change the sign of the sum
+    const double orient = signed_volume < 0.0 ? -1.0 : 1.0;
     const int G = std::max(4, std::min(192, (int)std::floor(2.0 / std::max(mean_edge, 1e-6))));
     const double h = 2.0 / G;
     auto cellc = [&](double x) { return std::max(0, std::min(G - 1, (int)std::floor((x + 1.0) / h))); };
@@ -1495,7 +1499,7 @@ int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* f
     a.M = M; a.V = V; a.F = F;
     a.pts = ctx->d_w_pts.as<double>(); a.from = ctx->d_w_from.as<double>(); a.to = ctx->d_w_to.as<double>(); a.tris = ctx->d_w_tris.as<int>();
     a.grid.G = G; a.grid.inv_h = 1.0 / h; a.grid.cell_start = ctx->d_w_start.as<int>(); a.grid.items = ctx->d_w_items.as<int>();
-    a.radius = radius;
+    a.radius = radius; a.orient = orient;
     a.out = ctx->d_w_out.as<double>();
     a.w_out = w_out ? a.out + (size_t)3 * M : nullptr;
     a.tri_out = tri_out ? reinterpret_cast<int*>(a.out + (size_t)6 * M) : nullptr;

@@ -62,8 +62,10 @@ def test_mesh_interpolate_parity(built, cp_level, deform):
 
 @pytest.mark.gpu
 def test_mesh_interpolate_accepts_either_winding(built):
-    """msm_mesh_interpolate promises "any closed spherical triangle mesh": faces wound inward (two corners swapped) locate the
-    same triangles and give the same result as the outward-wound mesh."""
+    """msm_mesh_interpolate promises "any closed spherical triangle mesh": a mesh whose faces are wound inward as a whole (two
+    corners of every face swapped) locates the same triangles and gives the same result as the outward-wound mesh.  (Single
+    flipped faces of a FOLDED mesh are a different matter: they keep losing to their neighbours, as in the oracle's locator —
+    the groupwise producers rely on that, tests/test_gpu_group.py.)"""
     from msm_newmeshreg_b200 import Context
     cxyz0, ctris = pyorc.icosphere(3)
     _, _, mvd = pyorc.spacings(cxyz0, ctris)
@@ -74,12 +76,11 @@ def test_mesh_interpolate_accepts_either_winding(built):
     ctx = Context()
     out, tri, w = ctx.mesh_interpolate(pts, start, ctris, end, details=True)
     flipped = ctris[:, [0, 2, 1]].copy()
-    mixed = ctris.copy(); mixed[::2] = flipped[::2]
-    for faces in (flipped, mixed):
-        o2, t2, w2 = ctx.mesh_interpolate(pts, start, faces, end, details=True)
-        interior = w.min(1) > 1e-9
-        assert np.array_equal(t2[interior], tri[interior])
-        assert np.abs(o2 - out).max() < 1e-9
+    o2, t2, w2 = ctx.mesh_interpolate(pts, start, flipped, end, details=True)
+    interior = w.min(1) > 1e-9
+    assert np.array_equal(t2[interior], tri[interior])
+    assert np.abs(o2 - out).max() < 1e-9
+    assert np.abs(w2[:, [0, 2, 1]] - w).max() < 1e-9          # weights follow the face's own vertex order
     ctx.close()
 
 
