@@ -6,8 +6,10 @@
 // combination of the END mesh's vertices and push it back onto the sphere of radius RAD.
 //
 // The START mesh is NOT a regular icosphere (it is the current, deformed control grid), so the icosahedral hierarchy of
-// locate.cuh does not apply; a uniform voxel grid over unit directions (built on the host: control grids are small)
-// gives each query a handful of candidate triangles.
+// locate.cuh does not apply; a uniform voxel grid over unit directions gives each query a handful of candidate triangles.
+// The grid is built on the device (k_tri_cells count / fill around one scan, cell lists then put in ascending triangle order
+// so that exact ties between neighbouring faces are decided the same way every run): the same call also serves the data-mesh
+// sized point locations of metric_resample (ico6 / ico7 meshes, millions of cells).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -33,6 +35,40 @@ struct WarpArgs {
     int* tri_out;          // optional [M]
     double* w_out;         // optional [M][3]
 };
+
+// One thread per triangle: the cells its (bulge-expanded) bounding box of unit directions touches.  FILL = false: count per
+// cell; FILL = true: write the triangle id at cell_start[cell] + (running fill count).
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_tri_cells(int F, int G, double inv_h, const double* __restrict__ xyz, const int* __restrict__ tris,
+                                                   int* __restrict__ counts, const int* __restrict__ cell_start, int* __restrict__ fill,
+                                                   int* __restrict__ items) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= F) return;
+    double u[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const double* p = xyz + 3 * tris[3 * t + j];
+        const double n = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+        u[j][0] = p[0] / n; u[j][1] = p[1] / n; u[j][2] = p[2] / n;
+    }
+    auto d2 = [](const double* x, const double* y) { return (x[0] - y[0]) * (x[0] - y[0]) + (x[1] - y[1]) * (x[1] - y[1]) + (x[2] - y[2]) * (x[2] - y[2]); };
+    const double emax2 = fmax(d2(u[0], u[1]), fmax(d2(u[1], u[2]), d2(u[2], u[0])));
+    const double sag = 1.0 - sqrt(fmax(0.0, 1.0 - emax2 / 3.0)) + 1e-9;   // how far the spherical triangle bulges out of its flat box
+    int lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double mn = fmin(u[0][d], fmin(u[1][d], u[2][d])) - sag, mx = fmax(u[0][d], fmax(u[1][d], u[2][d])) + sag;
+        lo[d] = max(0, min(G - 1, (int)floor((mn + 1.0) * inv_h)));
+        hi[d] = max(0, min(G - 1, (int)floor((mx + 1.0) * inv_h)));
+    }
+    for (int x = lo[0]; x <= hi[0]; x++)
+        for (int y = lo[1]; y <= hi[1]; y++)
+            for (int z = lo[2]; z <= hi[2]; z++) {
+                const int c = (x * G + y) * G + z;
+                if (!FILL) atomicAdd(counts + c, 1);
+                else items[cell_start[c] + atomicAdd(fill + c, 1)] = t;
+            }
+}
 
 __device__ __forceinline__ void w_unit(const double* p, double* u) {
     const double n = sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);

@@ -146,7 +146,7 @@ struct msm_ctx {
     BinGrid pend_bg{};
     bool pend_binned = false;
 
-    DevBuf d_w_start, d_w_items, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
+    DevBuf d_w_start, d_w_items, d_w_items2, d_w_counts, d_w_fill, d_w_from, d_w_to, d_w_tris, d_w_pts, d_w_out;  // msm_mesh_interpolate
     // feature pre-processing (features.cuh): scratch of its own, so that a deferred patch build's voxel grid stays intact
     DevBuf d_f_in, d_f_ref, d_f_vals, d_f_mask, d_f_mask2, d_f_out, d_f_stats, d_f_cdf;
     DevBuf d_f_cell_counts, d_f_cell_start, d_f_cell_fill, d_f_cell_of, d_f_sorted, d_f_sorted2, d_f_scan;
@@ -1445,7 +1445,7 @@ int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* f
     CK(cudaSetDevice(ctx->device));
     if (M <= 0) return 0;
     if (V <= 0 || F <= 0) FAIL("msm_mesh_interpolate: empty mesh");
-    // voxel grid over unit directions, cell ~ mean edge; each triangle goes to every cell its (bulge-expanded) box touches
+    // voxel grid over unit directions, cell ~ mean edge (its size and the mesh's orientation from one host pass over the faces)
     std::vector<double> u((size_t)V * 3);
     for (int i = 0; i < V; i++) {
         const double n = std::sqrt(from_xyz[3 * i] * from_xyz[3 * i] + from_xyz[3 * i + 1] * from_xyz[3 * i + 1] + from_xyz[3 * i + 2] * from_xyz[3 * i + 2]);
@@ -1466,35 +1466,37 @@ int msm_mesh_interpolate(msm_ctx* ctx, const double* pts, int M, const double* f
     const double orient = signed_volume < 0.0 ? -1.0 : 1.0;
     const int G = std::max(4, std::min(192, (int)std::floor(2.0 / std::max(mean_edge, 1e-6))));
     const double h = 2.0 / G;
-    auto cellc = [&](double x) { return std::max(0, std::min(G - 1, (int)std::floor((x + 1.0) / h))); };
-    std::vector<int> start((size_t)G * G * G + 1, 0);
-    std::vector<std::array<int, 6>> box(F);
-    for (int t = 0; t < F; t++) {
-        const double* a = &u[3 * tris[3 * t]]; const double* b = &u[3 * tris[3 * t + 1]]; const double* c = &u[3 * tris[3 * t + 2]];
-        auto d2 = [](const double* x, const double* y) { return (x[0] - y[0]) * (x[0] - y[0]) + (x[1] - y[1]) * (x[1] - y[1]) + (x[2] - y[2]) * (x[2] - y[2]); };
-        const double emax2 = std::max(d2(a, b), std::max(d2(b, c), d2(c, a)));
-        const double sag = 1.0 - std::sqrt(std::max(0.0, 1.0 - emax2 / 3.0)) + 1e-9;
-        for (int d = 0; d < 3; d++) {
-            box[t][d] = cellc(std::min(a[d], std::min(b[d], c[d])) - sag);
-            box[t][3 + d] = cellc(std::max(a[d], std::max(b[d], c[d])) + sag);
-        }
-        for (int x = box[t][0]; x <= box[t][3]; x++)
-            for (int y = box[t][1]; y <= box[t][4]; y++)
-                for (int z = box[t][2]; z <= box[t][5]; z++) start[((size_t)x * G + y) * G + z + 1]++;
-    }
-    for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
-    std::vector<int> items(start.back()), fill(start.begin(), start.end() - 1);
-    for (int t = 0; t < F; t++)
-        for (int x = box[t][0]; x <= box[t][3]; x++)
-            for (int y = box[t][1]; y <= box[t][4]; y++)
-                for (int z = box[t][2]; z <= box[t][5]; z++) items[fill[((size_t)x * G + y) * G + z]++] = t;
-    if (upload(ctx, ctx->d_w_start, start.data(), start.size())) return 1;
-    if (upload(ctx, ctx->d_w_items, items.data(), items.size())) return 1;
     if (upload(ctx, ctx->d_w_from, from_xyz, (size_t)V * 3)) return 1;
     if (upload(ctx, ctx->d_w_to, to_xyz, (size_t)V * 3)) return 1;
     if (upload(ctx, ctx->d_w_tris, tris, (size_t)F * 3)) return 1;
     if (upload(ctx, ctx->d_w_pts, pts, (size_t)M * 3)) return 1;
     CK(ctx->d_w_out.ensure((size_t)M * (24 + 24 + 4)));
+    {   // voxel grid of the triangles, on the device: count, scan, fill, cell lists into ascending triangle order
+        const size_t nc = (size_t)G * G * G;
+        CK(ctx->d_w_counts.ensure(nc * 4)); CK(ctx->d_w_start.ensure((nc + 1) * 4)); CK(ctx->d_w_fill.ensure(nc * 4));
+        CK(cudaMemsetAsync(ctx->d_w_counts.p, 0, nc * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_w_fill.p, 0, nc * 4, ctx->stream));
+        Timer tm(ctx, "mesh_grid");
+        k_tri_cells<false><<<(F + 127) / 128, 128, 0, ctx->stream>>>(F, G, 1.0 / h, ctx->d_w_from.as<double>(), ctx->d_w_tris.as<int>(),
+                                                                    ctx->d_w_counts.as<int>(), nullptr, nullptr, nullptr);
+        KLAUNCH_CHECK();
+        const int nchunks = 148, chunk = ((int)nc + nchunks - 1) / nchunks;
+        CK(ctx->d_scan_sums.ensure((size_t)nchunks * 4));
+        k_scan_chunk_sums<<<nchunks, 256, 0, ctx->stream>>>((int)nc, chunk, ctx->d_w_counts.as<int>(), ctx->d_scan_sums.as<int>());
+        KLAUNCH_CHECK();
+        k_scan_chunk_apply<<<nchunks, 256, 0, ctx->stream>>>((int)nc, chunk, ctx->d_w_counts.as<int>(), ctx->d_scan_sums.as<int>(), ctx->d_w_start.as<int>());
+        KLAUNCH_CHECK();
+        // the length of the cell lists sizes their buffer (one 4-byte read-back; the point set's results are awaited below anyway)
+        int total = 0;
+        CK(cudaMemcpyAsync(&total, ctx->d_w_start.as<int>() + nc, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(ctx->d_w_items.ensure((size_t)std::max(total, 1) * 4)); CK(ctx->d_w_items2.ensure((size_t)std::max(total, 1) * 4));
+        k_tri_cells<true><<<(F + 127) / 128, 128, 0, ctx->stream>>>(F, G, 1.0 / h, ctx->d_w_from.as<double>(), ctx->d_w_tris.as<int>(), nullptr,
+                                                                   ctx->d_w_start.as<int>(), ctx->d_w_fill.as<int>(), ctx->d_w_items2.as<int>());
+        KLAUNCH_CHECK();
+        k_cell_rank_sort<<<(unsigned)((nc + 3) / 4), 128, 0, ctx->stream>>>((int)nc, ctx->d_w_start.as<int>(), ctx->d_w_items2.as<int>(), ctx->d_w_items.as<int>());
+        KLAUNCH_CHECK();
+    }
     WarpArgs a;
     a.M = M; a.V = V; a.F = F;
     a.pts = ctx->d_w_pts.as<double>(); a.from = ctx->d_w_from.as<double>(); a.to = ctx->d_w_to.as<double>(); a.tris = ctx->d_w_tris.as<int>();
