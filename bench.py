@@ -308,6 +308,34 @@ def level_wall(data_level, cp_level, C, arm, threads):
                           if arm == "gpu" else "reference Fusion.h / ELC.h / FastPD.h, unmodified")}
 
 
+# ---------------------------------------------------------------------------------------------- feature pre-processing
+def feature_preprocessing(arm, level=6, D=4):
+    """featurespace::initialize (src/featurespace.cc:18-65) of one resolution level — data of an irregular ico`level`-sized mesh
+    resampled onto the ico`level` template (adaptive barycentric), smoothed (sigma 5), histogram matched, variance normalised —
+    arm "gpu": the product's featurespace (host/src/featurespace.h over csrc/features.cuh); arm "reference": the reference's own
+    featurespace.cc + reg_tools.cpp compiled in place (oracle/_ref/libref_feat.so; the oracle port where that is absent).
+    Wall clock from host arrays to host arrays, mesh containers included on both sides."""
+    from msm_newmeshreg_b200 import host
+    xyz, tris = host.icosphere(level)
+    xi = smooth_warp(xyz, 5, 1.0)
+    rng = np.random.default_rng(3)
+    di = np.stack([2.0 + 1.5 * random_field(xi, 21 + d) + 0.3 * rng.normal(size=len(xi)) for d in range(D)])
+    dr = np.stack([-1.0 + 0.7 * random_field(xyz, 71 + d) + 0.3 * rng.normal(size=len(xyz)) for d in range(D)])
+    kw = dict(sigma=(5.0, 5.0), intensitynorm=True, varnorm=True)
+    if arm == "gpu":
+        fn, kind = host.featurespace_initialize, "b200"
+        fn(level, (xi, tris), di, (xyz, tris), dr, **kw)          # first call: CUDA context of the feature path, icosphere cache
+    else:
+        from oracle import pyorc, pyreffeat
+        fn, kind = (pyreffeat.featurespace_initialize, "reference") if pyreffeat.available() else (pyorc.featurespace_initialize, "port")
+    ts = []
+    for _ in range(3 if arm == "gpu" else 1):
+        t0 = time.perf_counter(); out = fn(level, (xi, tris), di, (xyz, tris), dr, **kw); ts.append(time.perf_counter() - t0)
+    return {"what": f"featurespace::initialize, ico{level} ({len(xyz)} vertices), {D} feature dimensions, sigma 5, histogram matching + "
+                    f"variance normalisation", "arm": arm, "kind": kind, "seconds": min(ts),
+            "checksum": float(np.abs(out[0]).sum() + np.abs(out[1]).sum())}
+
+
 # ---------------------------------------------------------------------------------------------- CP-sharded mode
 def bench_cp_sharded(args, rank, world, local, C, metric, unit, emit=True):
     """ONE HCP-scale registration (ico7 / ico5): control points and triplets split into contiguous ranges over the GPUs
@@ -682,6 +710,11 @@ def main():
                 line["level_wall"] = level_wall(args.data_level, args.cp_level, C, "reference", 1)
             except Exception as e:
                 line["level_wall"] = {"error": f"{type(e).__name__}: {e}"}
+        if args.secondary:
+            try:
+                line["feature_preprocessing"] = feature_preprocessing("reference")
+            except Exception as e:
+                line["feature_preprocessing"] = {"error": f"{type(e).__name__}: {e}"}
         emit_line(json.dumps(line))
         return
 
@@ -977,6 +1010,11 @@ def main():
             if world > 1:
                 dist.barrier()
     if rank == 0:
+        if args.secondary:
+            try:
+                secondary["feature_preprocessing"] = feature_preprocessing("gpu")
+            except Exception as e:
+                secondary["feature_preprocessing"] = {"error": f"{type(e).__name__}: {e}"}
         if secondary:
             line["secondary"] = secondary
         if args.level_wall and world == 1:

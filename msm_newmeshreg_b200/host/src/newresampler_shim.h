@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -145,20 +146,20 @@ public:
         for (int j = 0; j < 3; j++) T.set_vertex_no(j, topo_->F[t][j]);
         return T;
     }
-    std::vector<int>::const_iterator nbegin(int i) const { return topo_->nbr[i].begin(); }
-    std::vector<int>::const_iterator nend(int i) const { return topo_->nbr[i].end(); }
-    std::vector<int>::const_iterator tIDbegin(int i) const { return topo_->vtri[i].begin(); }
-    std::vector<int>::const_iterator tIDend(int i) const { return topo_->vtri[i].end(); }
-    int get_total_neighbours(int i) const { return (int)topo_->nbr[i].size(); }
+    std::vector<int>::const_iterator nbegin(int i) const { return adj().nbr[i].begin(); }
+    std::vector<int>::const_iterator nend(int i) const { return adj().nbr[i].end(); }
+    std::vector<int>::const_iterator tIDbegin(int i) const { return adj().vtri[i].begin(); }
+    std::vector<int>::const_iterator tIDend(int i) const { return adj().vtri[i].end(); }
+    int get_total_neighbours(int i) const { return (int)adj().nbr[i].size(); }
     int get_resolution() const { return resolution_; }
     double calculate_MaxVD() const {
         double mx = 0;
-        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) mx = std::max(mx, (V()[i] - V()[j]).norm());
+        for (int i = 0; i < nvertices(); i++) for (int j : adj().nbr[i]) mx = std::max(mx, (V()[i] - V()[j]).norm());
         return mx;
     }
     double calculate_MeanVD() const {
         double s = 0; long n = 0;
-        for (int i = 0; i < nvertices(); i++) for (int j : topo_->nbr[i]) { s += (V()[i] - V()[j]).norm(); n++; }
+        for (int i = 0; i < nvertices(); i++) for (int j : adj().nbr[i]) { s += (V()[i] - V()[j]).norm(); n++; }
         return n ? s / n : 0;
     }
     std::vector<std::vector<double>> get_face_angles() const {
@@ -180,8 +181,7 @@ public:
         for (int i = 0; i < nv; i++) (*V_)[i] = Point(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
         topo_->F.resize(nf);
         for (int t = 0; t < nf; t++) topo_->F[t] = {tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]};
-        resolution_ = resolution;
-        build_adjacency();
+        resolution_ = resolution;   // adjacency: built on first use (see adj())
     }
     // Point is standard layout {X, Y, Z}: the vertex array IS the flat [nv][3] coordinate array the C ABI takes
     const double* coord_data() const { static_assert(sizeof(Point) == 3 * sizeof(double), "Point must be three packed doubles"); return V().empty() ? nullptr : &V()[0].X; }
@@ -195,17 +195,10 @@ public:
         for (int t = 0; t < ntriangles(); t++) for (int j = 0; j < 3; j++) o[3 * t + j] = topo_->F[t][j];
         return o;
     }
-    // adjacency order: faces ascending; neighbours by first appearance over those faces
-    void build_adjacency() {
-        topo_->nbr.assign(V().size(), {}); topo_->vtri.assign(V().size(), {});
-        for (int t = 0; t < ntriangles(); t++) for (int j = 0; j < 3; j++) topo_->vtri[topo_->F[t][j]].push_back(t);
-        for (int v = 0; v < nvertices(); v++)
-            for (int t : topo_->vtri[v])
-                for (int j = 0; j < 3; j++) {
-                    int u = topo_->F[t][j];
-                    if (u != v && std::find(topo_->nbr[v].begin(), topo_->nbr[v].end(), u) == topo_->nbr[v].end()) topo_->nbr[v].push_back(u);
-                }
-    }
+    // adjacency order: faces ascending; neighbours by first appearance over those faces.  Built on first use and shared by all
+    // copies of the mesh: the data-sized meshes that only pass through resampling / point location never need it
+    // (56 ms for an ico7 mesh).
+    void build_adjacency() { (void)adj(); }
 private:
     // Coordinates are copy-on-write: the drivers copy meshes freely (reset_meshspace / reset_CPgrid / get_CPgrid take and
     // return meshes by value, src/DiscreteModel.h:108-119), a copy costs nothing until one side moves a vertex.  (Not for
@@ -220,15 +213,42 @@ private:
     // (reset_meshspace / reset_CPgrid take meshes by value semantics), only coordinates ever change
     struct Topo {
         std::vector<std::array<int, 3>> F;
-        std::vector<std::vector<int>> nbr, vtri;
+        mutable std::vector<std::vector<int>> nbr, vtri;
+        mutable std::once_flag adjacency_once;
     };
+    const Topo& adj() const {
+        const Topo& T = *topo_;
+        const size_t nv = V().size();
+        std::call_once(T.adjacency_once, [&T, nv] {
+            T.nbr.assign(nv, {}); T.vtri.assign(nv, {});
+            for (int t = 0; t < (int)T.F.size(); t++) for (int j = 0; j < 3; j++) T.vtri[T.F[t][j]].push_back(t);
+            for (int v = 0; v < (int)nv; v++)
+                for (int t : T.vtri[v])
+                    for (int j = 0; j < 3; j++) {
+                        const int u = T.F[t][j];
+                        if (u != v && std::find(T.nbr[v].begin(), T.nbr[v].end(), u) == T.nbr[v].end()) T.nbr[v].push_back(u);
+                    }
+        });
+        return T;
+    }
     std::shared_ptr<Topo> topo_ = std::make_shared<Topo>();
     std::shared_ptr<NEWMAT::Matrix> pv_;
     int resolution_ = -1;
 };
 
 // make_mesh_from_icosa(k): k-times 4-split icosahedron, unit radius, nested numbering, child faces 4f..4f+3.
+inline Mesh make_mesh_from_icosa_uncached(int level);
+// Every level of a registration asks for the same few icospheres again (control grid, sampling grid, data template): built once
+// per level and handed out as copies (topology shared, coordinates copy-on-write) — ico7 costs 115 ms to build.
 inline Mesh make_mesh_from_icosa(int level) {
+    static std::mutex mtx;
+    static std::map<int, Mesh> cache;
+    std::lock_guard<std::mutex> lock(mtx);
+    auto it = cache.find(level);
+    if (it == cache.end()) it = cache.emplace(level, make_mesh_from_icosa_uncached(level)).first;
+    return it->second;
+}
+inline Mesh make_mesh_from_icosa_uncached(int level) {
     const double t = (1.0 + std::sqrt(5.0)) / 2.0;
     const double base[12][3] = {{-1, t, 0}, {1, t, 0}, {-1, -t, 0}, {1, -t, 0}, {0, -1, t}, {0, 1, t},
                                 {0, -1, -t}, {0, 1, -t}, {t, 0, -1}, {t, 0, 1}, {-t, 0, -1}, {-t, 0, 1}};
