@@ -1081,7 +1081,9 @@ static int unary_launch(msm_ctx* ctx, float* d_out, const PeerSet& peers) {
         s.pcx = ctx->d_pcx.as<float>(); s.pcy = ctx->d_pcy.as<float>(); s.pcz = ctx->d_pcz.as<float>();
         k_cp_hint<<<(Ns + 127) / 128, 128, 0, ctx->stream>>>(s, Ns);
         KLAUNCH_CHECK();
-        k_unary_setup<<<(Ns + 3) / 4, 128, 0, ctx->stream>>>(s, Ns);
+        const size_t setup_smem = (size_t)4 * L * 15 * sizeof(double);   // per warp: K block + output block of one control point
+        const int staged = setup_smem <= 48 * 1024 ? 1 : 0;
+        k_unary_setup<<<(Ns + 3) / 4, 128, staged ? setup_smem : 0, ctx->stream>>>(s, Ns, staged);
         KLAUNCH_CHECK();
     }
 #define LAUNCH_UNARY(Q)                                                                                             \

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_cp_hint(UnarySetupArgs a, int Ns) {
 
 // One WARP per control point (4 per CTA, no block barrier): from the hint face's dual basis A (k_cp_hint found the face),
 //     per sample i :  c_i = A CP_k + A r_i     and     per label l :  M_l = A K_kl,  g_l = A K_kl CP_k.
-__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
+__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns, int staged) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= Ns) return;   // whole warps leave together
@@ -117,11 +117,23 @@ __global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
         a.pcy[s] = (float)(x1 + (A[3] * x + A[4] * y + A[5] * z));
         a.pcz[s] = (float)(x2 + (A[6] * x + A[7] * y + A[8] * z));
     }
+    // Per label: the control point's block of K (L x 9 doubles) and its output block (L x 12 floats) are contiguous, but a lane
+    // working on label l touches them with strides of 72 / 48 bytes (12 sectors per request, ncu r6).  With `staged` the warp
+    // moves both blocks through its slice of shared memory with coalesced requests; the arithmetic is the same either way.
+    extern __shared__ double s_setup[];
+    double* sK = s_setup + (size_t)(threadIdx.x >> 5) * a.L * 15;      // [L][9] doubles, then [L][12] floats (= 6 doubles per label)
+    float* sO = reinterpret_cast<float*>(sK + (size_t)a.L * 9);
+    const double* Kg = a.Kd + (size_t)k * a.L * 9;
+    float* og = a.lab12 + (size_t)row * a.L * 12;
+    if (staged) {
+        for (int i = lane; i < a.L * 9; i += 32) sK[i] = Kg[i];
+        __syncwarp();
+    }
     for (int l = lane; l < a.L; l += 32) {
-        const double* K = a.Kd + ((size_t)k * a.L + l) * 9;
+        const double* K = (staged ? sK : Kg) + l * 9;
         // the control point itself moves by (R-I) CP_k (no cancellation: K holds R-I at full precision)
         const double dx = K[0] * ox + K[1] * oy + K[2] * oz, dy = K[3] * ox + K[4] * oy + K[5] * oz, dz = K[6] * ox + K[7] * oy + K[8] * oz;
-        float* o = a.lab12 + ((size_t)row * a.L + l) * 12;
+        float* o = (staged ? sO : og) + l * 12;
 #pragma unroll
         for (int r = 0; r < 3; r++) {
             const double A0 = A[3 * r], A1 = A[3 * r + 1], A2 = A[3 * r + 2];
@@ -130,6 +142,10 @@ __global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns) {
             o[3 * r + 2] = (float)(A0 * K[2] + A1 * K[5] + A2 * K[8]);
             o[9 + r] = (float)(A0 * dx + A1 * dy + A2 * dz);
         }
+    }
+    if (staged) {
+        __syncwarp();
+        for (int i = lane; i < a.L * 12; i += 32) og[i] = sO[i];
     }
 }
 

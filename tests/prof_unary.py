@@ -16,6 +16,7 @@ P = pb.make_problem(data_level, cp_level, C, seed=1, warp=0.3, deform_cp=0.1)
 ctx = pb.gpu_context(P)
 ctx.set_timing(True)
 ctx.build_patches()
+ctx.build_patches()      # second build of a level: the one-pass path (fixed-capacity rows), what every later iteration sees
 off, idx = ctx.patches()
 ms = []
 main = []
