@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_cp_hint(UnarySetupArgs a, int Ns) {
 
 // One WARP per control point (4 per CTA, no block barrier): from the hint face's dual basis A (k_cp_hint found the face),
 //     per sample i :  c_i = A CP_k + A r_i     and     per label l :  M_l = A K_kl,  g_l = A K_kl CP_k.
-__global__ void __launch_bounds__(128) k_unary_setup(UnarySetupArgs a, int Ns, int staged) {
+__global__ void __launch_bounds__(128, 8) k_unary_setup(UnarySetupArgs a, int Ns, int staged) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= Ns) return;   // whole warps leave together
