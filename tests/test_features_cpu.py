@@ -121,3 +121,25 @@ def test_reference_rejects_masks_on_foreign_vertices_like_the_port():
         pyorc.featurespace_initialize(3, mi, di, mr, dr, exclude=True)
     with pytest.raises(RuntimeError):
         pyreffeat.featurespace_initialize(3, mi, di, mr, dr, exclude=True)
+
+
+# ------------------------------------------------------------------------------------------------ committed golden vectors
+def _golden():
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_features", os.path.join(here, "golden", "make_golden_features.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    return mg, np.load(os.path.join(here, "golden", "features.npz"))
+
+
+@pytest.mark.parametrize("name", ["defaults_ico3", "normalised_ico3", "masked_own_vertices"])
+def test_port_reproduces_the_committed_reference_output(name):
+    """tests/golden/features.npz was written by the reference's own featurespace (tests/golden/make_golden_features.py); it
+    travels to boxes where oracle/_ref cannot be rebuilt."""
+    mg, gold = _golden()
+    mi, di, mr, dr, ico, opt = mg.inputs(name)
+    a, b, ea, eb = pyorc.featurespace_initialize(ico, mi, di, mr, dr, **opt)
+    assert np.abs(a - gold[f"{name}/input"]).max() < 1e-12 and np.abs(b - gold[f"{name}/reference"]).max() < 1e-12
+    if ea is not None:
+        assert np.array_equal(ea, gold[f"{name}/excl_input"]) and np.array_equal(eb, gold[f"{name}/excl_reference"])

@@ -118,3 +118,21 @@ def test_featurespace_errors(built):
     mi, di, mr, dr = fi.make(4, 3, D=1, seed=12)
     with pytest.raises(host.HostError):
         host.featurespace_initialize(3, mi, di, mr, dr, exclude=True)     # masks need data on the template's vertices
+
+
+@pytest.mark.parametrize("name", ["defaults_ico3", "normalised_ico3", "masked_own_vertices"])
+def test_featurespace_initialize_against_golden_fixture(built, name):
+    """The product's featurespace::initialize against tests/golden/features.npz — the output of the reference's own
+    featurespace.cc on the same inputs (tests/golden/make_golden_features.py)."""
+    import importlib.util
+    import os
+    from msm_newmeshreg_b200 import host
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_features", os.path.join(here, "golden", "make_golden_features.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "features.npz"))
+    mi, di, mr, dr, ico, opt = mg.inputs(name)
+    a, b, ea, eb = host.featurespace_initialize(ico, mi, di, mr, dr, **opt)
+    assert np.abs(a - gold[f"{name}/input"]).max() < 1e-10 and np.abs(b - gold[f"{name}/reference"]).max() < 1e-10
+    if ea is not None:
+        assert np.array_equal(ea, gold[f"{name}/excl_input"]) and np.array_equal(eb, gold[f"{name}/excl_reference"])
