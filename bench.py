@@ -118,6 +118,32 @@ class Subject:
         self.sxyz = smooth_warp(txyz, seed + 100, 0.3 * cp_spacing)
 
 
+# ---------------------------------------------------------------------------------------------- NUMA placement of a rank
+def bind_to_gpu_numa_node(index, world):
+    """Multi-GPU runs: pin this rank's host threads to the CPU cores of its GPU's NUMA node (NVML's ideal CPU affinity) BEFORE any
+    pinned buffer is allocated, so that staging buffers are first-touched on the node the GPU hangs off and the end-to-end leg's
+    copies do not cross the socket interconnect.  MSM_BENCH_BIND=0 switches it off.  Returns a description for the bench line."""
+    if os.environ.get("MSM_BENCH_BIND", "1") == "0":
+        return {"bound": False, "why": "MSM_BENCH_BIND=0"}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        allowed = os.sched_getaffinity(0)
+
+        def cpus_of(i):
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), (ncpu + 63) // 64)
+            return {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1} & allowed
+        cpus = cpus_of(index)
+        if not cpus or cpus == allowed:
+            return {"bound": False, "why": "one NUMA node / no affinity information", "cpus": len(allowed)}
+        sharing = sum(1 for i in range(world) if cpus_of(i) == cpus)     # ranks whose GPUs hang off the same node share its cores
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": len(cpus), "of": len(allowed), "ranks_on_node": max(1, sharing)}
+    except Exception as e:   # no NVML, no permission: run unbound
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 # ---------------------------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -719,6 +745,7 @@ def main():
         return
 
     # ------------------------------------------------------------------ B200 arm
+    numa = bind_to_gpu_numa_node(local, world) if world > 1 else {"bound": False, "why": "single GPU"}
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -938,7 +965,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return evals_per_subject * B * world / float(t.item())
 
-    e2e_threads = args.e2e_threads if args.e2e_threads > 0 else max(1, (os.cpu_count() or 1) // world)
+    cores_here = len(os.sched_getaffinity(0)) if numa.get("bound") else (os.cpu_count() or 1) // world
+    ranks_sharing = numa.get("ranks_on_node", 1) if numa.get("bound") else 1
+    e2e_threads = args.e2e_threads if args.e2e_threads > 0 else max(1, cores_here // ranks_sharing)
     e2e_threads = max(1, min(B, e2e_threads))
     e2e_serial = time_e2e(1)
     e2e_value = time_e2e(e2e_threads) if e2e_threads > 1 else e2e_serial
@@ -973,7 +1002,7 @@ def main():
                          "algorithmic_bytes_per_launch": float(np.mean(alg_bytes_unary)), "avg_launch_ms": unary_ms, "launches_timed": un,
                          "triplet_moves_avg_ms": tm_ / max(tn_, 1)},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e,
-                    "host_threads": e2e_threads, "value_one_host_thread": e2e_serial,
+                    "host_threads": e2e_threads, "value_one_host_thread": e2e_serial, "numa": numa,
                     "api": "NonLinearSRegDiscreteModel::reset_meshspace/reset_CPgrid/setupCostFunction + computeTripletMoves"},
             "gpu_launches": int(launches), "clocks": clocks,
             "value_tables_only": value_tables_only, "ms_per_step_tables_only": ms_tables_only,
