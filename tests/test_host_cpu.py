@@ -262,3 +262,22 @@ def test_reference_driver_loop_compiles_against_the_mirror():
     lib = ctypes.CDLL(so)
     for name in ("ref_driver_run_discrete_opt", "ref_run_discrete_opt", "ref_fusion_model", "ref_fastpd_model", "msmhost_featurespace_initialize"):
         assert hasattr(lib, name), name
+
+
+def test_bench_numa_binding_degrades_gracefully():
+    """bench.py binds multi-GPU ranks to the cores of their GPU's NUMA node; without NVML / without a second node it must say
+    so and leave the process unbound."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    r = bench.bind_to_gpu_numa_node(0, 2)
+    assert r["bound"] is False and "why" in r
+    assert os.sched_getaffinity(0) == before
+    os.environ["MSM_BENCH_BIND"] = "0"
+    try:
+        assert bench.bind_to_gpu_numa_node(0, 2) == {"bound": False, "why": "MSM_BENCH_BIND=0"}
+    finally:
+        os.environ.pop("MSM_BENCH_BIND")
