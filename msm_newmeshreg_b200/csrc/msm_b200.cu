@@ -1584,7 +1584,7 @@ int msm_histogram_match(msm_ctx* ctx, double* data, int V, const double* data_re
                         const double* excl_ref, int excl_ref_rows, int bins) {
     CK(cudaSetDevice(ctx->device));
     if (V <= 0 || Vref <= 0 || D <= 0) FAIL("msm_histogram_match: empty input");
-    if (bins < 2 || bins > 4096) FAIL("msm_histogram_match: bins must be in [2, 4096]");
+    if (bins < 2 || bins > 2048) FAIL("msm_histogram_match: bins must be in [2, 2048] (both CDFs are staged in 48 KB of shared memory; the reference uses 256)");
     if (V >= (1 << 24) || Vref >= (1 << 24)) FAIL("msm_histogram_match: more than 2^24 values per dimension (the reference counts them in a float)");
     if ((excl && excl_rows < 1) || (excl_ref && excl_ref_rows < 1)) FAIL("msm_histogram_match: mask rows");
     if (upload(ctx, ctx->d_f_vals, data, (size_t)D * V)) return 1;
