@@ -281,3 +281,54 @@ def test_bench_numa_binding_degrades_gracefully():
         assert bench.bind_to_gpu_numa_node(0, 2) == {"bound": False, "why": "MSM_BENCH_BIND=0"}
     finally:
         os.environ.pop("MSM_BENCH_BIND")
+
+
+# ------------------------------------------------------------------------------------------------ mesh container of the mirror (CPU)
+@pytest.fixture(scope="module")
+def shim():
+    """tests/cpu_shim.cpp: host/src/newresampler_shim.h behind a small C ABI (header-only, no GPU library needed)."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out_dir = os.path.join(here, "_build"); os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libcpu_shim.so")
+    src = os.path.join(here, "cpu_shim.cpp")
+    hdr = os.path.join(here, "..", "msm_newmeshreg_b200", "host", "src", "newresampler_shim.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", src, "-o", so])
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize("level", [0, 2, 4])
+def test_mirror_icosphere_and_lazy_adjacency_match_the_oracle(shim, level):
+    """make_mesh_from_icosa of the mirror (cached per level) = the oracle's ([EXT] A7 numbering); the adjacency the mirror builds on
+    first use has the oracle's order — faces ascending, neighbours by first appearance — which label_sampling_grid's
+    breadth-first sweep (src/DiscreteModel.cpp:105-162) depends on."""
+    from oracle import pyorc
+    ox, ot = pyorc.icosphere(level, 1.0)
+    nv, nf = ctypes.c_int(), ctypes.c_int()
+    shim.shim_icosphere(level, ctypes.byref(nv), ctypes.byref(nf), None, None)
+    assert (nv.value, nf.value) == (len(ox), len(ot))
+    xyz = np.empty((nv.value, 3)); tris = np.empty((nf.value, 3), np.int32)
+    shim.shim_icosphere(level, ctypes.byref(nv), ctypes.byref(nf), xyz.ctypes.data_as(ctypes.c_void_p), tris.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(tris, ot) and np.abs(xyz - ox).max() < 1e-15
+    noff = np.empty(len(xyz) + 1, np.int32); toff = np.empty(len(xyz) + 1, np.int32)
+    nbr = np.empty(6 * len(xyz), np.int32); tri = np.empty(6 * len(xyz), np.int32)
+    shim.shim_adjacency(xyz.ctypes.data_as(ctypes.c_void_p), len(xyz), tris.ctypes.data_as(ctypes.c_void_p), len(tris),
+                        noff.ctypes.data_as(ctypes.c_void_p), nbr.ctypes.data_as(ctypes.c_void_p), toff.ctypes.data_as(ctypes.c_void_p),
+                        tri.ctypes.data_as(ctypes.c_void_p))
+    for v in range(len(xyz)):
+        inc = [t for t in range(len(tris)) if v in tris[t]] if level <= 2 else None
+        if inc is not None:
+            assert list(tri[toff[v]:toff[v + 1]]) == inc
+            seen = []
+            for t in inc:
+                for u in tris[t]:
+                    if u != v and u not in seen:
+                        seen.append(int(u))
+            assert list(nbr[noff[v]:noff[v + 1]]) == seen
+    deg = np.diff(noff)
+    assert (deg == 5).sum() == 12 and set(np.unique(deg)) <= {5, 6} and np.array_equal(deg, np.diff(toff))
+
+
+def test_mirror_mesh_copies_are_independent(shim):
+    assert shim.shim_semantics(3) == 0
