@@ -626,17 +626,10 @@ def group_data_term(args, rank, world, local):
     t2 = time.perf_counter()
     if world > 1:
         mine = torch.from_numpy(np.stack([m.rotated_all(s) for s in range(s0, s1)])).cuda()
-        per = (S + world - 1) // world
-        pad = torch.zeros((per, m.L, m.Vt), dtype=torch.float64, device="cuda")
-        pad[:s1 - s0] = mine
-        allv = torch.empty((world * per, m.L, m.Vt), dtype=torch.float64, device="cuda")
-        dist.all_gather_into_tensor(allv, pad)
-        allv = allv.cpu().numpy()
-        for r in range(world):
-            a, b = sharding.shard_range(S, r, world)
-            if r != rank:
-                for s in range(a, b):
-                    m.set_rotated(s, allv[r * per + (s - a)])
+        allv = sharding.allgather_subject_rows(mine, S).cpu().numpy()     # ONE all-gather of the [S][L][V_t] values (NCCL)
+        for s in range(S):
+            if not (s0 <= s < s1):
+                m.set_rotated(s, allv[s])
     t3 = time.perf_counter()
     if world > 1:
         m.finish_setup()                                 # patch maps of every subject -> CSR -> device

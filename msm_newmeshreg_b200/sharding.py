@@ -51,3 +51,29 @@ def assemble_label_major(slices, n):
     sizes = shard_sizes(n, world)
     assert all(s.shape[1] == sizes[r] for r, s in enumerate(slices))
     return np.concatenate(slices, axis=1)
+
+
+def allgather_subject_rows(mine, n_subjects, group=None):
+    """Groupwise registration, subjects sharded contiguously (shard_range): every rank contributes the rows of ITS subjects,
+    mine[s_local, ...] (e.g. the [L][V_template] resampled values of src/DiscreteGroupModel.cpp:92), and receives all of them in
+    subject order: returns a tensor [n_subjects, ...].  ONE fixed-size all_gather (shards are padded to the largest one), on CUDA
+    tensors (NCCL) or CPU tensors (gloo)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        assert mine.shape[0] == n_subjects
+        return mine
+    rank = dist.get_rank(group)
+    s0, s1 = shard_range(n_subjects, rank, world)
+    assert mine.shape[0] == s1 - s0, "rows of this rank's subjects expected"
+    per = max(shard_sizes(n_subjects, world))
+    pad = torch.zeros((per,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    pad[: s1 - s0] = mine
+    allv = torch.empty((world * per,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(allv, pad, group=group)
+    rows = []
+    for r in range(world):
+        a, b = shard_range(n_subjects, r, world)
+        rows.append(allv[r * per: r * per + (b - a)])
+    return torch.cat(rows, dim=0)

@@ -125,6 +125,36 @@ def test_allgather_label_major_gloo_world2():
     assert all(t == float(world) for _, _, t in res)
 
 
+def _gloo_subject_worker(rank, world, port, S, shape, q):
+    import torch
+    import torch.distributed as dist
+    from msm_newmeshreg_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    s0, s1 = sharding.shard_range(S, rank, world)
+    full = torch.arange(S * int(np.prod(shape)), dtype=torch.float64).reshape((S,) + shape)
+    got = sharding.allgather_subject_rows(full[s0:s1].clone(), S)
+    q.put((rank, bool(torch.equal(got, full)), tuple(got.shape)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("S", [4, 3, 1])
+def test_allgather_subject_rows_gloo_world2(S):
+    """Groupwise data term over 2 ranks: contiguous subject shards, uneven (S = 3) and with an empty shard (S = 1),
+    come back as [S][L][V] in subject order from ONE all-gather."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 29621 + S
+    procs = [ctx.Process(target=_gloo_subject_worker, args=(r, world, port, S, (3, 5), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res) and all(shape == (S, 3, 5) for _, _, shape in res)
+
+
 def test_assemble_label_major_numpy():
     from msm_newmeshreg_b200 import sharding as sh
     full = np.arange(19 * 10).reshape(19, 10)
